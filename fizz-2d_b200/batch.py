@@ -1,0 +1,376 @@
+"""Batched entry point: thousands to millions of independent Fizz-2D worlds advanced in lockstep on one B200.
+
+`BatchedWorld` is the batched counterpart of the reference's `physics.World` (physics.py:30-301):
+`.step(n)` = n x `World.update()` for every world, `.energy()` = `World.energy()`, `.dump_world(i)` =
+`str(world)`.  World state lives in one device slab per *group* (worlds sharing a scene topology), owned by a
+torch tensor; all compute goes through the C-ABI of libfizz_b200.so (include/fizz_b200.h).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from . import scene as _scene
+
+
+class GroupSpec:
+    """Host-side description of one group: topology + fixed geometry + per-world SoA initial conditions."""
+
+    def __init__(self, scene: _scene.Scene, points: Sequence[np.ndarray], velocity: np.ndarray,
+                 density: np.ndarray, gravity=(0.0, 0.0), max_calls=4096, check_valid=True):
+        """points[b]: (W, n_b, 2) vertices of free body b per world; velocity: (W, F, 2); density: (W, F)."""
+        self.scene = scene
+        self.width, self.height = scene.width, scene.height
+        F = len(points)
+        W = points[0].shape[0]
+        self.n_worlds, self.n_free, self.n_fixed = W, F, scene.n_fixed
+        self.nverts_free = [p.shape[1] for p in points]
+        self.nverts_fixed = [len(p) for p in scene.fixed]
+        eps = scene.params.get("EPSILON", _scene.DEFAULT_PARAMS["EPSILON"])
+        V = sum(self.nverts_free)
+        self.pos = np.empty((2 * F, W))
+        self.vel = np.empty((2 * F, W))
+        self.off = np.empty((2 * V, W))
+        self.radius = np.empty((F, W))
+        self.mass = np.empty((F, W))
+        valid = np.ones(W, dtype=bool)
+        v0 = 0
+        for b, P in enumerate(points):
+            c = _scene.polygon_constants(P, density[:, b], eps)
+            self.pos[2 * b], self.pos[2 * b + 1] = c["com"][:, 0], c["com"][:, 1]
+            self.vel[2 * b], self.vel[2 * b + 1] = velocity[:, b, 0], velocity[:, b, 1]
+            n = P.shape[1]
+            for v in range(n):
+                self.off[2 * (v0 + v)] = c["offx"][:, v]
+                self.off[2 * (v0 + v) + 1] = c["offy"][:, v]
+            v0 += n
+            self.radius[b] = c["radius"]
+            self.mass[b] = c["mass"]
+            valid &= c["valid"]
+        self.valid = valid
+        if check_valid and not valid.all():
+            raise ValueError("%d world(s) hold a degenerate polygon (NaN/zero inertia or a vertex on the centroid): "
+                             "the reference turns those into NaN on step 1 (SURVEY Q13)" % int((~valid).sum()))
+        self.thr = _scene.sqrt_threshold(self.radius)
+        # fixed bodies (FixedPolygon -> Polygon.__init__ -> Obj.__init__: centroid and radius the same way)
+        self.fixed_xy = np.concatenate(scene.fixed, axis=0) if scene.fixed else np.zeros((0, 2))
+        self.fixed_com = np.zeros((self.n_fixed, 2))
+        self.fixed_radius = np.zeros(self.n_fixed)
+        for j, pts in enumerate(scene.fixed):
+            c = _scene.polygon_constants(pts[None], None)
+            self.fixed_com[j] = c["com"][0]
+            self.fixed_radius[j] = c["radius"][0]
+        self.fixed_thr = _scene.sqrt_threshold(self.fixed_radius)
+        self.params = _scene.resolve_params(scene.params, gravity, scene.height, max_calls)
+
+    @classmethod
+    def from_scene(cls, scene: _scene.Scene, n_worlds=1, deltas: Optional[np.ndarray] = None, **kw):
+        """Replicate a scene n_worlds times; deltas (W,F,4) = per-body (dx,dy,dvx,dvy) (scene.perturbation_deltas)."""
+        F = scene.n_free
+        if deltas is None:
+            deltas = np.zeros((n_worlds, F, 4))
+        assert deltas.shape == (n_worlds, F, 4)
+        points, vel, dens = [], np.empty((n_worlds, F, 2)), np.empty((n_worlds, F))
+        for b, body in enumerate(scene.free):
+            P = body.points[None, :, :] + deltas[:, b, None, 0:2]
+            points.append(np.ascontiguousarray(P))
+            vel[:, b, :] = body.velocity[None, :] + deltas[:, b, 2:4]
+            dens[:, b] = body.density
+        return cls(scene, points, vel, dens, **kw)
+
+
+class _Group:
+    def __init__(self, spec: GroupSpec, device: int, world_ids: np.ndarray):
+        import torch
+        self.spec = spec
+        self.world_ids = world_ids
+        L = _lib.load()
+        nverts = np.ascontiguousarray(spec.nverts_free + spec.nverts_fixed, dtype=np.int32)
+        self._keep = (nverts, np.ascontiguousarray(spec.fixed_xy), np.ascontiguousarray(spec.fixed_com),
+                      np.ascontiguousarray(spec.fixed_thr))
+        self.desc = _lib.FizzGroupDesc(
+            n_free=spec.n_free, n_fixed=spec.n_fixed, nverts=nverts.ctypes.data_as(_lib.ip),
+            fixed_xy=_lib.as_dp(self._keep[1]), fixed_com=_lib.as_dp(self._keep[2]),
+            fixed_thr=_lib.as_dp(self._keep[3]), params=spec.params)
+        self.layout = _lib.FizzLayout()
+        _lib.check(L.fizz_layout(C.byref(self.desc), spec.n_worlds, C.byref(self.layout)))
+        if not torch.cuda.is_available():
+            raise _lib.FizzError("no CUDA device: the batched engine has no CPU fallback")
+        self.device = device
+        self.slab = torch.zeros(self.layout.total_words, dtype=torch.float64, device="cuda:%d" % device)
+        h = C.c_void_p()
+        _lib.check(L.fizz_group_create(C.byref(self.desc), spec.n_worlds, device, C.c_void_p(self.slab.data_ptr()),
+                                       self.layout.total_words, C.byref(h)))
+        self.handle = h
+        self.trace = None
+
+    def close(self):
+        if self.handle:
+            _lib.load().fizz_group_destroy(self.handle)
+            self.handle = None
+
+    def upload(self, stream=0):
+        s = self.spec
+        arrs = [np.ascontiguousarray(a) for a in (s.pos, s.vel, s.off, s.thr, s.mass)]
+        _lib.check(_lib.load().fizz_upload(self.handle, *[_lib.as_dp(a) for a in arrs], C.c_void_p(stream)))
+        self._held = arrs
+
+    def section(self, name, rows, dtype=None):
+        """Zero-copy torch view [rows, W] of a slab section."""
+        import torch
+        L = self.layout
+        o = getattr(L, name)
+        t = self.slab[o:o + rows * L.stride].view(rows, L.stride)[:, :L.n_worlds]
+        if dtype is not None:
+            t = self.slab[o:o + rows * L.stride].view(dtype).view(rows, L.stride)[:, :L.n_worlds]
+        return t
+
+    def enable_trace(self, capacity):
+        import torch
+        self.trace = (torch.zeros(capacity * 6, dtype=torch.int64, device=self.slab.device),
+                      torch.zeros(1, dtype=torch.int64, device=self.slab.device), capacity)
+        _lib.check(_lib.load().fizz_set_trace(self.handle, C.c_void_p(self.trace[0].data_ptr()), capacity,
+                                              C.c_void_p(self.trace[1].data_ptr())))
+
+    def read_trace(self):
+        import torch
+        torch.cuda.synchronize(self.slab.device)
+        n = int(self.trace[1].item())
+        if n > self.trace[2]:
+            raise _lib.FizzError("contact trace overflow: %d > %d" % (n, self.trace[2]))
+        raw = self.trace[0][:n * 6].cpu().numpy().tobytes()
+        recs = (_lib.FizzContact * n).from_buffer_copy(raw)
+        out = [(int(self.world_ids[r.world]), r.step, r.call, r.i, r.j, r.nx, r.ny, r.mag) for r in recs]
+        out.sort(key=lambda r: r[:5])
+        return out
+
+
+class BatchedWorld:
+    """W independent worlds.  World index order is the order given at construction; groups are an internal
+    partition by scene topology (mixed batches keep one resident scene descriptor per group)."""
+
+    def __init__(self, specs: Sequence[GroupSpec], world_ids: Optional[Sequence[np.ndarray]] = None, device: int = 0):
+        import torch
+        self.device = device
+        torch.cuda.set_device(device)
+        if world_ids is None:
+            world_ids, o = [], 0
+            for s in specs:
+                world_ids.append(np.arange(o, o + s.n_worlds))
+                o += s.n_worlds
+        self.groups: List[_Group] = [_Group(s, device, np.asarray(ids)) for s, ids in zip(specs, world_ids)]
+        self.n_worlds = sum(s.n_worlds for s in specs)
+        self._where = {}
+        for gi, g in enumerate(self.groups):
+            for k, wid in enumerate(g.world_ids):
+                if self.n_worlds <= 1 << 16:
+                    self._where[int(wid)] = (gi, k)
+        self.streams = [torch.cuda.Stream(device=device) for _ in self.groups] if len(self.groups) > 1 else [None]
+        self.steps_requested = 0
+        self.upload()
+
+    # -- construction ------------------------------------------------------------------------------------
+    @classmethod
+    def from_in(cls, path, n_worlds=1, perturb=False, seed=0, dpos=5.0, dvel=30.0, gravity=(0.0, 0.0),
+                max_calls=4096, device=0):
+        sc = _scene.load_in(path)
+        deltas = _scene.perturbation_deltas(seed, n_worlds, sc.n_free, dpos, dvel) if perturb else None
+        return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls)], device=device)
+
+    @classmethod
+    def from_text(cls, text, n_worlds=1, deltas=None, gravity=(0.0, 0.0), max_calls=4096, device=0):
+        sc = _scene.parse_in(text)
+        return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls)], device=device)
+
+    def close(self):
+        for g in self.groups:
+            g.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- stepping ----------------------------------------------------------------------------------------
+    def _stream_ptr(self, k):
+        st = self.streams[k] if k < len(self.streams) else None
+        if st is None:
+            import torch
+            return torch.cuda.current_stream(self.device).cuda_stream
+        return st.cuda_stream
+
+    def upload(self):
+        """(Re)load the initial conditions: host -> device, resets heat/status/step counters."""
+        for k, g in enumerate(self.groups):
+            g.upload(self._stream_ptr(k))
+        self.steps_requested = 0
+        self.synchronize()
+
+    def step(self, n_steps=1):
+        """n_steps x World.update() for every world; one kernel launch per group (groups run concurrently)."""
+        L = _lib.load()
+        for k, g in enumerate(self.groups):
+            _lib.check(L.fizz_step(g.handle, int(n_steps), C.c_void_p(self._stream_ptr(k))))
+        self.steps_requested += int(n_steps)
+
+    def synchronize(self):
+        import torch
+        torch.cuda.synchronize(self.device)
+
+    # -- readback ----------------------------------------------------------------------------------------
+    def _gather(self, fn, shape_tail, dtype=np.float64):
+        out = np.empty((self.n_worlds,) + shape_tail, dtype=dtype)
+        for g in self.groups:
+            out[g.world_ids] = fn(g)
+        return out
+
+    def _download(self, g, k, **want):
+        s = g.spec
+        W, F, V = s.n_worlds, s.n_free, sum(s.nverts_free)
+        bufs = dict(pos=np.empty((2 * F, W)) if want.get("pos") else None,
+                    vel=np.empty((2 * F, W)) if want.get("vel") else None,
+                    heat=np.empty(W) if want.get("heat") else None,
+                    energy=np.empty((4, W)) if want.get("energy") else None,
+                    verts=np.empty((2 * V, W)) if want.get("verts") else None)
+        ibufs = dict(status=np.empty(W, dtype=np.int64) if want.get("status") else None,
+                     steps=np.empty(W, dtype=np.int64) if want.get("steps") else None,
+                     calls=np.empty(W, dtype=np.int64) if want.get("calls") else None)
+
+        def p(a, t):
+            return a.ctypes.data_as(t) if a is not None else None
+        _lib.check(_lib.load().fizz_download(
+            g.handle, p(bufs["pos"], _lib.dp), p(bufs["vel"], _lib.dp), p(bufs["heat"], _lib.dp),
+            p(bufs["energy"], _lib.dp), p(bufs["verts"], _lib.dp), p(ibufs["status"], _lib.lp),
+            p(ibufs["steps"], _lib.lp), p(ibufs["calls"], _lib.lp), C.c_void_p(self._stream_ptr(k))))
+        bufs.update(ibufs)
+        return bufs
+
+    def download(self, **want):
+        res = [self._download(g, k, **want) for k, g in enumerate(self.groups)]
+        self.synchronize()
+        return res
+
+    def energy(self):
+        """(W, 4): total, kinetic, potential, heat -- World.energy() of every world (physics.py:66-74)."""
+        res = self.download(energy=True)
+        out = np.empty((self.n_worlds, 4))
+        for g, r in zip(self.groups, res):
+            out[g.world_ids] = r["energy"].T
+        return out
+
+    def heat(self):
+        res = self.download(heat=True)
+        out = np.empty(self.n_worlds)
+        for g, r in zip(self.groups, res):
+            out[g.world_ids] = r["heat"]
+        return out
+
+    def status(self):
+        res = self.download(status=True)
+        out = np.empty(self.n_worlds, dtype=np.int64)
+        for g, r in zip(self.groups, res):
+            out[g.world_ids] = r["status"]
+        return out
+
+    def steps_done(self):
+        res = self.download(steps=True)
+        out = np.empty(self.n_worlds, dtype=np.int64)
+        for g, r in zip(self.groups, res):
+            out[g.world_ids] = r["steps"]
+        return out
+
+    def calls(self):
+        res = self.download(calls=True)
+        out = np.empty(self.n_worlds, dtype=np.int64)
+        for g, r in zip(self.groups, res):
+            out[g.world_ids] = r["calls"]
+        return out
+
+    def com(self):
+        """List (one entry per group) of (W_g, F_g, 4) arrays: com.pos.x, com.pos.y, com.vel.x, com.vel.y.
+        For a single-group batch returns the array itself."""
+        res = self.download(pos=True, vel=True)
+        outs = []
+        for g, r in zip(self.groups, res):
+            F = g.spec.n_free
+            a = np.empty((g.spec.n_worlds, F, 4))
+            a[:, :, 0] = r["pos"][0::2].T
+            a[:, :, 1] = r["pos"][1::2].T
+            a[:, :, 2] = r["vel"][0::2].T
+            a[:, :, 3] = r["vel"][1::2].T
+            outs.append(a)
+        return outs[0] if len(outs) == 1 else outs
+
+    def vertices(self):
+        """List per group of (W_g, V_g, 2) free-vertex positions (point.pos) after the last step()."""
+        res = self.download(verts=True)
+        outs = []
+        for g, r in zip(self.groups, res):
+            V = sum(g.spec.nverts_free)
+            a = np.empty((g.spec.n_worlds, V, 2))
+            a[:, :, 0] = r["verts"][0::2].T
+            a[:, :, 1] = r["verts"][1::2].T
+            outs.append(a)
+        return outs[0] if len(outs) == 1 else outs
+
+    def dump_world(self, i, verts=None):
+        """str(world) of world i (physics.py:291-301, :713-722, :600-606): int() truncation, clamp to the frame."""
+        gi, k = self._where[int(i)]
+        g = self.groups[gi]
+        if verts is None:
+            verts = self.vertices()
+            verts = verts if len(self.groups) == 1 else verts[gi]
+        return format_world(g.spec, verts[k])
+
+    # -- contact trace (tests) ---------------------------------------------------------------------------
+    def enable_trace(self, capacity=1 << 20):
+        for g in self.groups:
+            g.enable_trace(capacity)
+
+    def contacts(self):
+        out = []
+        for g in self.groups:
+            out += g.read_trace()
+        out.sort(key=lambda r: r[:5])
+        return out
+
+    def kernel_info(self):
+        info = []
+        for g in self.groups:
+            r, s, t, b = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            n = C.c_int64()
+            _lib.check(_lib.load().fizz_kernel_info(g.handle, C.byref(r), C.byref(s), C.byref(t), C.byref(b), C.byref(n)))
+            info.append(dict(regs=r.value, smem=s.value, threads=t.value, blocks_per_sm=b.value, launches=n.value))
+        return info
+
+
+def _fmt_point(x, y, w, h):
+    # Point.__str__ (physics.py:600-606)
+    bx = max(min(int(x), w - 1), 0)
+    by = max(min(int(y), h - 1), 0)
+    return "point," + str(bx) + "," + str(by)
+
+
+def format_world(spec: GroupSpec, verts: np.ndarray) -> str:
+    """World.__str__ for one world given its (V,2) free-vertex array."""
+    out = str(spec.width) + "," + str(spec.height) + "\n"
+    o = 0
+    for n in spec.nverts_free:
+        out += "polygon\nsides," + str(n) + "\n" + \
+            "\n".join(_fmt_point(verts[o + k, 0], verts[o + k, 1], spec.width, spec.height) for k in range(n)) + "\n"
+        o += n
+    for pts in spec.scene.fixed:
+        out += "polygon\nsides," + str(len(pts)) + "\n" + \
+            "\n".join(_fmt_point(p[0], p[1], spec.width, spec.height) for p in pts) + "\n"
+    return out
+
+
+def fp64_peak(device=0, iters=4096):
+    """Measured FP64 FMA throughput of the device in TFLOP/s (roofline denominator)."""
+    t, ms = C.c_double(), C.c_double()
+    _lib.check(_lib.load().fizz_fp64_peak(device, iters, C.byref(t), C.byref(ms)))
+    return t.value, ms.value

@@ -1,0 +1,95 @@
+"""ctypes binding of the C-ABI in include/fizz_b200.h (libfizz_b200.so, built in-tree by build.py).
+
+There is no fallback: if the shared library is missing or a CUDA call fails, the error propagates.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfizz_b200.so")
+
+MAX_FREE, MAX_FIXED, MAX_POLY_VERTS, MAX_FIXED_VERTS, MAX_HITS = 8, 16, 16, 96, 32
+ST_RUNNING, ST_CAPPED, ST_NONFINITE, ST_HIT_OVERFLOW = 0, 1, 2, 3
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+lp = C.POINTER(C.c_int64)
+
+
+class FizzParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "elasticity", "epsilon", "time_tol", "collision_tol", "vibrate_tol", "time_disc", "gx", "gy",
+        "one_plus_e", "one_minus_e2", "acc_x", "acc_y", "height")] + [("max_calls", C.c_int32), ("reserved", C.c_int32)]
+
+
+class FizzGroupDesc(C.Structure):
+    _fields_ = [("n_free", C.c_int32), ("n_fixed", C.c_int32), ("nverts", ip), ("fixed_xy", dp),
+                ("fixed_com", dp), ("fixed_thr", dp), ("params", FizzParams)]
+
+
+class FizzLayout(C.Structure):
+    _fields_ = [("n_worlds", C.c_int64), ("stride", C.c_int64),
+                ("n_free", C.c_int32), ("n_fixed", C.c_int32), ("n_free_verts", C.c_int32), ("reserved", C.c_int32)] + \
+               [(n, C.c_int64) for n in ("pos", "vel", "heat", "status", "steps", "calls", "state_words",
+                                         "off", "thr", "mass", "verts", "energy", "total_words")]
+
+
+class FizzContact(C.Structure):
+    _fields_ = [("world", C.c_int64), ("step", C.c_int32), ("call", C.c_int32), ("i", C.c_int32), ("j", C.c_int32),
+                ("nx", C.c_double), ("ny", C.c_double), ("mag", C.c_double)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "fizz_abi_version": (C.c_int, []),
+    "fizz_last_error": (C.c_char_p, []),
+    "fizz_host_norm2": (None, [C.c_int64, dp, dp, dp]),
+    "fizz_host_dot2": (None, [C.c_int64, dp, dp, dp, dp, dp]),
+    "fizz_host_sqrt_threshold": (None, [C.c_int64, dp, dp]),
+    "fizz_layout": (C.c_int, [C.POINTER(FizzGroupDesc), C.c_int64, C.POINTER(FizzLayout)]),
+    "fizz_group_create": (C.c_int, [C.POINTER(FizzGroupDesc), C.c_int64, C.c_int, C.c_void_p, C.c_int64,
+                                    C.POINTER(C.c_void_p)]),
+    "fizz_group_destroy": (C.c_int, [C.c_void_p]),
+    "fizz_upload": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp, C.c_void_p]),
+    "fizz_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "fizz_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fizz_download": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp, lp, lp, lp, C.c_void_p]),
+    "fizz_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fizz_kernel_info": (C.c_int, [C.c_void_p, ip, ip, ip, ip, lp]),
+    "fizz_fp64_peak": (C.c_int, [C.c_int, C.c_int32, dp, dp]),
+}
+
+_lib = None
+
+
+class FizzError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libfizz_b200.so (raises if it has not been built: run `python -m fizz2d_b200.build` or
+    `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise FizzError("CUDA extension %s is missing; build it with __graft_entry__.build()" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.fizz_abi_version() != 1:
+            raise FizzError("ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise FizzError("fizz_b200 error %d: %s" % (rc, load().fizz_last_error().decode()))
+
+
+def as_dp(a):
+    return a.ctypes.data_as(dp)

@@ -1,0 +1,165 @@
+/* fizz_b200.h -- C-ABI of the B200-native batched stepping engine for Fizz-2D's hot path.
+ *
+ * The reference (BKaperick/Fizz-2D) has NO plugin / FFI layer: the hot path is the Python method
+ * `World.update()` (src/physics.py:76-259) called from `main.py:98`.  This header is therefore the boundary a
+ * maintainer would bind with ctypes from a batched driver (see INTEGRATION.md for the stub); every entry point
+ * cites the reference interface it stands in for.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Model: a *group* is W independent worlds that share one scene topology (F free polygons with fixed vertex
+ * counts, X fixed polygons, one parameter set).  World state lives in ONE caller-owned device slab of 8-byte
+ * words, structure-of-arrays with the world index fastest (row stride Wp = W rounded up to 128), so a warp's 32
+ * worlds read 256 contiguous bytes per row.  The caller allocates the slab (e.g. a torch tensor), the library
+ * only borrows the pointer.  All calls return 0 on success or a negative FIZZ_E_* code; fizz_last_error()
+ * gives the message.  There is no CPU fallback: without a CUDA device every device call fails.
+ */
+#ifndef FIZZ_B200_H
+#define FIZZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIZZ_ABI_VERSION 1
+
+#define FIZZ_MAX_FREE 8          /* free polygons per world (kernel instantiations F = 1..8)        */
+#define FIZZ_MAX_FIXED 16        /* fixed polygons per scene                                         */
+#define FIZZ_MAX_POLY_VERTS 16   /* vertices per polygon                                             */
+#define FIZZ_MAX_FIXED_VERTS 96  /* total fixed vertices per scene (staged in shared memory)         */
+#define FIZZ_MAX_HITS 32         /* contact tuples one check_collisions() may return per world       */
+
+/* error codes */
+#define FIZZ_OK 0
+#define FIZZ_E_ARG (-1)     /* bad argument / unsupported shape */
+#define FIZZ_E_CUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
+#define FIZZ_E_STATE (-3)   /* call sequence error (e.g. step before upload) */
+
+/* per-world status word (slab section `status`) */
+#define FIZZ_ST_RUNNING 0
+#define FIZZ_ST_CAPPED 1    /* resolve loop wanted more than max_calls check_collisions in one update() */
+#define FIZZ_ST_NONFINITE 2 /* a centre of mass became NaN/inf; world frozen at end of launch   */
+#define FIZZ_ST_HIT_OVERFLOW 3 /* more than FIZZ_MAX_HITS simultaneous contact tuples; world frozen */
+
+/* Tunables of the reference read at call time inside update() (physics.py:19-25; set by `PARAM` lines,
+ * main.py:39-41) plus the two constructor arguments of World that matter (physics.py:32-33).  The three
+ * derived fields are evaluated by the HOST in Python so that they are bit-identical to the Python float
+ * expressions of the reference (physics.py:188,191,516). */
+typedef struct FizzParams {
+    double elasticity;     /* ELASTICITY  */
+    double epsilon;        /* EPSILON     */
+    double time_tol;       /* TIME_TOL    */
+    double collision_tol;  /* COLLISION_TOL */
+    double vibrate_tol;    /* VIBRATE_TOL */
+    double time_disc;      /* World.time_disc (0.05) */
+    double gx, gy;         /* World.global_accel / GRAVITY; (0,0) for every .in scene */
+    double one_plus_e;     /* (1+ELASTICITY)                */
+    double one_minus_e2;   /* (1-ELASTICITY**2)             */
+    double acc_x, acc_y;   /* sum([1*global_accel])/1  -> the acceleration Point.move() installs (physics.py:516) */
+    double height;         /* World.height, for p_energy (physics.py:373) */
+    int32_t max_calls;     /* watchdog: state-relevant check_collisions() calls per update(); >= 32 */
+    int32_t reserved;
+} FizzParams;
+
+/* Scene topology + fixed geometry of one group (host pointers, read during fizz_group_create only).
+ * Replaces the object graph main.read_input() builds (main.py:23-83): `world.objs`, `world.fixed_objs`. */
+typedef struct FizzGroupDesc {
+    int32_t n_free;              /* F: len(world.objs)       */
+    int32_t n_fixed;             /* X: len(world.fixed_objs) */
+    const int32_t *nverts;       /* [F+X] vertices per polygon, free bodies first (physics.py:270 order) */
+    const double *fixed_xy;      /* fixed vertices x,y interleaved, polygons concatenated (FixedPolygon.points) */
+    const double *fixed_com;     /* [X][2] centroids (physics.py:314)  */
+    const double *fixed_thr;     /* [X] broad-phase thresholds T(radius): largest s with sqrt(s) <= radius */
+    FizzParams params;
+} FizzGroupDesc;
+
+/* Word offsets (units of 8 bytes) of every section inside the device slab.  Row r of a section starts at
+ * offset + r*Wp; element w of the row is world w.  Doubles unless noted. */
+typedef struct FizzLayout {
+    int64_t n_worlds;   /* W  */
+    int64_t stride;     /* Wp */
+    int32_t n_free, n_fixed, n_free_verts, reserved;
+    /* dynamic state (contiguous: [pos .. calls]) */
+    int64_t pos;        /* [F*2] com.pos  x,y per free body        (physics.py:315)  */
+    int64_t vel;        /* [F*2] com.vel                                              */
+    int64_t heat;       /* [1]   world.heat                        (physics.py:53,195) */
+    int64_t status;     /* [1]   int64 FIZZ_ST_*                                       */
+    int64_t steps;      /* [1]   int64 completed update() calls                        */
+    int64_t calls;      /* [1]   int64 state-relevant check_collisions() calls, lifetime */
+    int64_t state_words;/* words from `pos` to the end of `calls` */
+    /* per-world constants */
+    int64_t off;        /* [V*2] |r|cos(phi), |r|sin(phi) per free vertex (physics.py:358-359,632-635) */
+    int64_t thr;        /* [F]   T(obj.radius) per free body        (physics.py:322,277-278) */
+    int64_t mass;       /* [F]   obj.mass = area*density            (physics.py:624) */
+    /* outputs */
+    int64_t verts;      /* [V*2] point.pos of every free vertex after the last completed launch */
+    int64_t energy;     /* [4]   World.energy(): total,kinetic,potential,heat (physics.py:66-74) */
+    int64_t total_words;
+} FizzLayout;
+
+typedef struct FizzGroup FizzGroup;
+
+/* one recorded contact tuple (tests / debugging): the tuples check_collisions() returns (physics.py:288) */
+typedef struct FizzContact {
+    int64_t world;
+    int32_t step;   /* 0-based update() index                                  */
+    int32_t call;   /* 1-based state-relevant check_collisions() call in step  */
+    int32_t i, j;   /* indices into objs+fixed_objs                            */
+    double nx, ny, mag;
+} FizzContact;
+
+int fizz_abi_version(void);
+const char *fizz_last_error(void);
+
+/* Host helpers implementing numpy's 2-vector contract for the Python loader's init-time math:
+ *   norm2: sqrt(fma(y,y,x*x))   == np.linalg.norm([x,y])      (physics.py:322,633,358)
+ *   dot2 : fma(a1,b1,a0*b0)     == np.dot([a0,a1],[b0,b1])    */
+void fizz_host_norm2(int64_t n, const double *x, const double *y, double *out);
+void fizz_host_dot2(int64_t n, const double *a0, const double *a1, const double *b0, const double *b1, double *out);
+/* T(r): largest double s such that sqrt(s) <= r, so that `norm(d) > r` (physics.py:278) == `fma(dy,dy,dx*dx) > T(r)` */
+void fizz_host_sqrt_threshold(int64_t n, const double *r, double *out);
+
+/* Slab layout for a group of n_worlds worlds.  Pure host arithmetic. */
+int fizz_layout(const FizzGroupDesc *desc, int64_t n_worlds, FizzLayout *out);
+
+/* Bind a group to a caller-owned device slab of at least layout.total_words 8-byte words on `device`.
+ * Stands in for constructing `physics.World(width,height)` + its objects (main.py:28,68-77). */
+int fizz_group_create(const FizzGroupDesc *desc, int64_t n_worlds, int device, void *dev_slab, int64_t slab_words,
+                      FizzGroup **out);
+int fizz_group_destroy(FizzGroup *g);
+
+/* Host -> device initial conditions and per-world constants, SoA rows of length W (not Wp) in host memory:
+ * pos[F*2][W], vel[F*2][W], off[V*2][W], thr[F][W], mass[F][W].  Also zeroes heat/status/steps/calls.
+ * Asynchronous on `stream` (a cudaStream_t; 0 = default stream); host buffers must stay valid until the
+ * stream is synchronised (use pinned memory for true overlap). */
+int fizz_upload(FizzGroup *g, const double *pos, const double *vel, const double *off, const double *thr,
+                const double *mass, void *stream);
+
+/* Advance every running world by n_steps World.update() calls (physics.py:76-259) in ONE kernel launch;
+ * state stays in registers/shared memory for the whole launch.  Asynchronous on `stream`. */
+int fizz_step(FizzGroup *g, int64_t n_steps, void *stream);
+
+/* World.energy() for every world into the slab's `energy` section (physics.py:66-74). Asynchronous. */
+int fizz_energy(FizzGroup *g, void *stream);
+
+/* Device -> host: any pointer may be NULL.  pos/vel [F*2][W], heat [W], energy [4][W] (runs fizz_energy first),
+ * verts [V*2][W], status/steps/calls int64 [W].  Asynchronous on `stream`. */
+int fizz_download(FizzGroup *g, double *pos, double *vel, double *heat, double *energy, double *verts,
+                  int64_t *status, int64_t *steps, int64_t *calls, void *stream);
+
+/* Optional contact trace for parity tests: device buffer of `capacity` FizzContact records + a device int64
+ * counter (both caller-owned); pass NULL to disable.  The counter may exceed capacity (overflow is dropped). */
+int fizz_set_trace(FizzGroup *g, void *dev_records, int64_t capacity, void *dev_counter);
+
+/* Introspection for bench/roofline reporting. */
+int fizz_kernel_info(FizzGroup *g, int32_t *regs_per_thread, int32_t *smem_bytes_per_block, int32_t *block_threads,
+                     int32_t *blocks_per_sm, int64_t *launches);
+
+/* FP64 FMA throughput microbenchmark (the roofline denominator MEASURED_PEAKS.json lacks): runs `iters`
+ * dependent-chain DFMA rounds on every SM of `device` and returns achieved TFLOP/s (FMA = 2 flops). */
+int fizz_fp64_peak(int device, int32_t iters, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIZZ_B200_H */
