@@ -338,13 +338,57 @@ class BatchedWorld:
         out.sort(key=lambda r: r[:5])
         return out
 
+    def set_tuning(self, mode="hybrid", chunk_steps=256):
+        """Execution strategy (results never depend on it): "hybrid" = ballistic thread-per-world kernel +
+        warp-per-world contact kernel per chunk of timesteps; "thread" = one thread-per-world kernel."""
+        m = {"hybrid": _lib.MODE_HYBRID, "thread": _lib.MODE_THREAD}[mode]
+        for g in self.groups:
+            _lib.check(_lib.load().fizz_set_tuning(g.handle, m, int(chunk_steps)))
+
+    def snapshot(self):
+        """Device-resident copy of the dynamic state of every group (replay without a host round trip)."""
+        import torch
+        snaps = []
+        for k, g in enumerate(self.groups):
+            t = torch.empty(g.layout.state_words, dtype=torch.float64, device=g.slab.device)
+            _lib.check(_lib.load().fizz_snapshot(g.handle, C.c_void_p(t.data_ptr()), C.c_void_p(self._stream_ptr(k))))
+            snaps.append(t)
+        return (snaps, self.steps_requested)
+
+    def restore(self, snap):
+        snaps, steps = snap
+        for k, (g, t) in enumerate(zip(self.groups, snaps)):
+            _lib.check(_lib.load().fizz_restore(g.handle, C.c_void_p(t.data_ptr()), int(steps),
+                                                C.c_void_p(self._stream_ptr(k))))
+        self.steps_requested = steps
+
+    def set_profiling(self, enabled=True):
+        for g in self.groups:
+            _lib.check(_lib.load().fizz_set_profiling(g.handle, 1 if enabled else 0))
+
+    def profile(self, reset=True):
+        """Per group: dict kernel -> (milliseconds, launches), device-timed with CUDA events inside fizz_step."""
+        out = []
+        for g in self.groups:
+            ms = (C.c_double * 3)()
+            n = (C.c_int64 * 3)()
+            _lib.check(_lib.load().fizz_profile_read(g.handle, ms, n, 1 if reset else 0))
+            out.append({"thread": (ms[0], n[0]), "ballistic": (ms[1], n[1]), "contact": (ms[2], n[2])})
+        return out
+
     def kernel_info(self):
         info = []
         for g in self.groups:
-            r, s, t, b = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
-            n = C.c_int64()
-            _lib.check(_lib.load().fizz_kernel_info(g.handle, C.byref(r), C.byref(s), C.byref(t), C.byref(b), C.byref(n)))
-            info.append(dict(regs=r.value, smem=s.value, threads=t.value, blocks_per_sm=b.value, launches=n.value))
+            d = {}
+            for name, which in (("thread", _lib.KERNEL_THREAD), ("ballistic", _lib.KERNEL_BALLISTIC),
+                                ("contact", _lib.KERNEL_CONTACT)):
+                r, s, t, b = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+                n = C.c_int64()
+                _lib.check(_lib.load().fizz_kernel_info(g.handle, which, C.byref(r), C.byref(s), C.byref(t), C.byref(b),
+                                                        C.byref(n)))
+                d[name] = dict(regs=r.value, smem=s.value, threads=t.value, blocks_per_sm=b.value)
+                d["launches"] = n.value
+            info.append(d)
         return info
 
 

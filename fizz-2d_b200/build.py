@@ -19,7 +19,8 @@ def needs_build():
     if not os.path.isfile(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SRC + [os.path.join(ROOT, "include", "fizz_b200.h")]
+    import glob
+    deps = SRC + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + [os.path.join(ROOT, "include", "fizz_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -1,0 +1,86 @@
+// fizz_ballistic_kernel.cuh -- thread-per-world kernel for QUIESCENT timesteps ("hybrid" mode, stage 1).
+//
+// A timestep whose broad phase (physics.py:272-281) lets no pair through is: one check_collisions() that returns
+// [], i.e. max overlap 0 on the first halving trial (:99-129), then finish_update (:237-239).  State-wise that is
+// a velocity-Verlet move of every centre of mass (Point.move :502-529) and nothing else -- vertices are derived
+// state.  This kernel advances each world through such steps with com position/velocity and the
+// per-body thresholds in registers (F is a template parameter: everything is unrolled, fixed-body constants come
+// straight from the kernel-parameter constant bank), and STOPS a world at the first step whose broad phase is
+// not empty; the warp-per-world contact kernel picks those worlds up from there (fizz_contact_kernel.cuh).
+// The broad phase of step t reads the snapshot obj.pos written at the end of step t-1, which at a
+// step boundary equals com.pos, so no separate snapshot is kept here.  Step 0 is never taken here: before the
+// first finish_update obj.pos aliases com.pos and the broad phase sees the MOVED position (SURVEY Q4 exception).
+#pragma once
+
+#include "fizz_common.cuh"
+
+namespace fizz {
+
+constexpr int BALLISTIC_BLOCK = 128;
+
+template <int F>
+__global__ void __launch_bounds__(BALLISTIC_BLOCK) ballistic_kernel(const __grid_constant__ KParams kp) {
+    const long long w = (long long)blockIdx.x * BALLISTIC_BLOCK + threadIdx.x;
+    if (w >= kp.W) return;
+    if (kp.status[w] != 0) return;
+    const long long step0 = kp.steps[w];
+    if (step0 == 0 || step0 >= kp.target_steps) return;
+    const long long Wp = kp.Wp;
+    const int X = kp.X;
+    double px[F], py[F], vx[F], vy[F], thr[F];
+#pragma unroll
+    for (int b = 0; b < F; b++) {
+        px[b] = kp.pos[(2 * b) * Wp + w];
+        py[b] = kp.pos[(2 * b + 1) * Wp + w];
+        vx[b] = kp.vel[(2 * b) * Wp + w];
+        vy[b] = kp.vel[(2 * b + 1) * Wp + w];
+        thr[b] = kp.thr[b * Wp + w];
+    }
+    const double dt = kp.time_disc;
+    long long step = step0;
+    while (step < kp.target_steps) {
+        // dist > max(r_i, r_j)  <=>  s > T(r_i) && s > T(r_j), s = fma(dy,dy,dx*dx)  (:277-278; T: see fizz_b200.h)
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < F; i++) {
+#pragma unroll
+            for (int j = i + 1; j < F; j++) {
+                const double dx = px[i] - px[j], dy = py[i] - py[j];
+                const double s = fma(dy, dy, dx * dx);
+                any |= !(s > thr[i] && s > thr[j]);
+            }
+        }
+        for (int j = 0; j < X; j++) {
+            const double cx = kp.fcx[j], cy = kp.fcy[j], ft = kp.fthr[j];
+#pragma unroll
+            for (int i = 0; i < F; i++) {
+                const double dx = px[i] - cx, dy = py[i] - cy;
+                const double s = fma(dy, dy, dx * dx);
+                any |= !(s > thr[i] && s > ft);
+            }
+        }
+        if (any) break;  // a pair reaches the narrow phase: hand the world to the contact kernel at this step
+#pragma unroll
+        for (int b = 0; b < F; b++) {
+            double nx_, ny_, nvx_, nvy_;
+            // every com holds the installed acceleration once step 0 is over
+            FIZZ_MOVE_POINT(px[b], py[b], vx[b], vy[b], dt, kp.accx, kp.accy, kp.accx, kp.accy, nx_, ny_, nvx_, nvy_);
+            px[b] = nx_; py[b] = ny_; vx[b] = nvx_; vy[b] = nvy_;
+        }
+        step++;
+    }
+    if (step != step0) {
+#pragma unroll
+        for (int b = 0; b < F; b++) {
+            kp.pos[(2 * b) * Wp + w] = px[b];
+            kp.pos[(2 * b + 1) * Wp + w] = py[b];
+            kp.vel[(2 * b) * Wp + w] = vx[b];
+            kp.vel[(2 * b + 1) * Wp + w] = vy[b];
+        }
+        kp.steps[w] = step;
+        kp.calls[w] += step - step0;  // one state-relevant check_collisions() per quiescent step
+        kp.vflag[w] = 0;              // vertices are derived: off + com
+    }
+}
+
+}  // namespace fizz

@@ -1,0 +1,64 @@
+// fizz_common.cuh -- shared declarations of the sm_100a stepping kernels.
+//
+// Reference semantics (file:line = /root/reference/src/physics.py): World.update :76-259, check_collisions
+// :262-289, polypoly_collision :765-840, Obj.pre_update :384-427, Point.move :502-529, Obj.reverse_update
+// :430-451, Obj.finish_update :453-464.  numpy's 2-vector dot/norm fuse the second product:
+// dot = fma(a1,b1,a0*b0), norm = sqrt(fma(a1,a1,a0*a0)).  Everything is compiled with -fmad=false so that no other
+// a*b+c is contracted; IEEE-754 division and square root are the CUDA defaults for double.
+#pragma once
+
+#include "fizz_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+namespace fizz {
+
+constexpr int TAB = FIZZ_MAX_FREE + FIZZ_MAX_FIXED;  // 24 bodies max
+constexpr int MAX_PAIRS = FIZZ_MAX_FREE * (FIZZ_MAX_FREE - 1) / 2 + FIZZ_MAX_FREE * FIZZ_MAX_FIXED;  // 156
+
+struct KParams {
+    // slab sections (row r of a section starts at ptr + r*Wp; element w of a row is world w)
+    double *pos, *vel, *heat;
+    long long *status, *steps, *calls, *vflag;
+    const double *off, *thr, *mass;
+    double *verts;
+    const double *fixed_geom;  // [FV][6]: x, y, unit normal of edge k->k+1 (nx, ny), own projection (lo, hi)
+    FizzContact *trace;
+    unsigned long long *trace_count;
+    long long trace_cap;
+    long long W, Wp, target_steps;
+    int F, X, V, FV;
+    int nv[TAB], vs[TAB];      // vertices per body / first vertex (free: into the world's rows, fixed: into fixed_geom)
+    double fcx[FIZZ_MAX_FIXED], fcy[FIZZ_MAX_FIXED], fthr[FIZZ_MAX_FIXED];
+    double coll_tol, time_tol, eps, vib_tol, time_disc, ope, ome2, accx, accy;
+    int max_calls;
+};
+
+__device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
+
+__device__ __forceinline__ void trace_hit(const KParams &kp, long long w, long long step, int call, int i, int j,
+                                          double nx, double ny, double mag) {
+    unsigned long long idx = atomicAdd(kp.trace_count, 1ULL);
+    if ((long long)idx < kp.trace_cap) {
+        FizzContact c;
+        c.world = w; c.step = (int)step; c.call = call; c.i = i; c.j = j; c.nx = nx; c.ny = ny; c.mag = mag;
+        kp.trace[idx] = c;
+    }
+}
+
+// Point.move (physics.py:502-529) of one centre of mass over `h`, starting acceleration (a0x, a0y); the move
+// installs the acceleration (accx, accy) = sum(forces)/mass (:516).
+//   halfdt = .5*dt ; uv = acc*halfdt ; va = vel + uv ; pos += va*dt ; acc = new ; vel = va + acc*halfdt
+#define FIZZ_MOVE_POINT(PX, PY, VX, VY, h, a0x, a0y, accx, accy, ox, oy, ovx, ovy)   \
+    {                                                                                \
+        const double halfdt_ = .5 * (h);                                             \
+        const double vax_ = (VX) + (a0x) * halfdt_, vay_ = (VY) + (a0y) * halfdt_;   \
+        ox = (PX) + vax_ * (h);                                                      \
+        oy = (PY) + vay_ * (h);                                                      \
+        ovx = vax_ + (accx) * halfdt_;                                               \
+        ovy = vay_ + (accy) * halfdt_;                                               \
+    }
+
+}  // namespace fizz

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, "libfizz_b200.so")
 
 MAX_FREE, MAX_FIXED, MAX_POLY_VERTS, MAX_FIXED_VERTS, MAX_HITS = 8, 16, 16, 96, 32
 ST_RUNNING, ST_CAPPED, ST_NONFINITE, ST_HIT_OVERFLOW = 0, 1, 2, 3
+MODE_THREAD, MODE_HYBRID = 0, 1
+KERNEL_THREAD, KERNEL_BALLISTIC, KERNEL_CONTACT = 0, 1, 2
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -32,8 +34,8 @@ class FizzGroupDesc(C.Structure):
 class FizzLayout(C.Structure):
     _fields_ = [("n_worlds", C.c_int64), ("stride", C.c_int64),
                 ("n_free", C.c_int32), ("n_fixed", C.c_int32), ("n_free_verts", C.c_int32), ("reserved", C.c_int32)] + \
-               [(n, C.c_int64) for n in ("pos", "vel", "heat", "status", "steps", "calls", "state_words",
-                                         "off", "thr", "mass", "verts", "energy", "total_words")]
+               [(n, C.c_int64) for n in ("pos", "vel", "heat", "status", "steps", "calls", "vflag", "state_words",
+                                         "off", "thr", "mass", "verts", "energy", "sched", "scene", "total_words")]
 
 
 class FizzContact(C.Structure):
@@ -57,7 +59,13 @@ EXPORTS = {
     "fizz_energy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fizz_download": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp, lp, lp, lp, C.c_void_p]),
     "fizz_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "fizz_kernel_info": (C.c_int, [C.c_void_p, ip, ip, ip, ip, lp]),
+    "fizz_kernel_info": (C.c_int, [C.c_void_p, C.c_int32, ip, ip, ip, ip, lp]),
+    "fizz_set_tuning": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
+    "fizz_snapshot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fizz_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fizz_vertices": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fizz_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fizz_profile_read": (C.c_int, [C.c_void_p, dp, lp, C.c_int32]),
     "fizz_fp64_peak": (C.c_int, [C.c_int, C.c_int32, dp, dp]),
 }
 

@@ -35,6 +35,14 @@ extern "C" {
 #define FIZZ_E_CUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
 #define FIZZ_E_STATE (-3)   /* call sequence error (e.g. step before upload) */
 
+/* execution modes (fizz_set_tuning) */
+#define FIZZ_MODE_HYBRID 1  /* ballistic thread-per-world kernel + warp-per-world contact kernel (default) */
+#define FIZZ_MODE_THREAD 0  /* one thread-per-world kernel with the full semantics                        */
+/* kernel ids (fizz_kernel_info) */
+#define FIZZ_KERNEL_THREAD 0
+#define FIZZ_KERNEL_BALLISTIC 1
+#define FIZZ_KERNEL_CONTACT 2
+
 /* per-world status word (slab section `status`) */
 #define FIZZ_ST_RUNNING 0
 #define FIZZ_ST_CAPPED 1    /* resolve loop wanted more than max_calls check_collisions in one update() */
@@ -86,7 +94,8 @@ typedef struct FizzLayout {
     int64_t status;     /* [1]   int64 FIZZ_ST_*                                       */
     int64_t steps;      /* [1]   int64 completed update() calls                        */
     int64_t calls;      /* [1]   int64 state-relevant check_collisions() calls, lifetime */
-    int64_t state_words;/* words from `pos` to the end of `calls` */
+    int64_t vflag;      /* [1]   int64 1 = `verts` holds explicit point.pos (pushed by a resolve pass), 0 = derived */
+    int64_t state_words;/* words from `pos` to the end of `vflag` */
     /* per-world constants */
     int64_t off;        /* [V*2] |r|cos(phi), |r|sin(phi) per free vertex (physics.py:358-359,632-635) */
     int64_t thr;        /* [F]   T(obj.radius) per free body        (physics.py:322,277-278) */
@@ -94,6 +103,9 @@ typedef struct FizzLayout {
     /* outputs */
     int64_t verts;      /* [V*2] point.pos of every free vertex after the last completed launch */
     int64_t energy;     /* [4]   World.energy(): total,kinetic,potential,heat (physics.py:66-74) */
+    /* library scratch (never touched by the caller) */
+    int64_t sched;      /* [1]+16 contact-kernel work list, count, cursor */
+    int64_t scene;      /* fixed-scene constants + vertex->body table     */
     int64_t total_words;
 } FizzLayout;
 
@@ -135,9 +147,23 @@ int fizz_group_destroy(FizzGroup *g);
 int fizz_upload(FizzGroup *g, const double *pos, const double *vel, const double *off, const double *thr,
                 const double *mass, void *stream);
 
-/* Advance every running world by n_steps World.update() calls (physics.py:76-259) in ONE kernel launch;
- * state stays in registers/shared memory for the whole launch.  Asynchronous on `stream`. */
+/* Advance every running world by n_steps World.update() calls (physics.py:76-259); stands in for the loop
+ * `for t in range(N): plane.update()` of main.py:97-98.  Asynchronous on `stream`, no host synchronisation.
+ * Hybrid mode: per chunk of timesteps one ballistic launch (thread per world, registers only), one work-list
+ * launch and one persistent contact launch (warp per world).  Thread mode: one launch for all n_steps. */
 int fizz_step(FizzGroup *g, int64_t n_steps, void *stream);
+
+/* Execution mode and timesteps per chunk (hybrid mode).  Results never depend on either. */
+int fizz_set_tuning(FizzGroup *g, int32_t mode, int64_t chunk_steps);
+
+/* Save / restore the dynamic state block (layout.state_words words starting at layout.pos) to / from a
+ * caller-owned device buffer, e.g. to replay a batch from its initial conditions without a host round trip.
+ * `steps_done` = the number of completed update() calls the restored state corresponds to. */
+int fizz_snapshot(FizzGroup *g, void *dev_dst, void *stream);
+int fizz_restore(FizzGroup *g, const void *dev_src, int64_t steps_done, void *stream);
+
+/* Make the slab's `verts` section current for every world (derives off+com where vflag == 0). Asynchronous. */
+int fizz_vertices(FizzGroup *g, void *stream);
 
 /* World.energy() for every world into the slab's `energy` section (physics.py:66-74). Asynchronous. */
 int fizz_energy(FizzGroup *g, void *stream);
@@ -151,9 +177,15 @@ int fizz_download(FizzGroup *g, double *pos, double *vel, double *heat, double *
  * counter (both caller-owned); pass NULL to disable.  The counter may exceed capacity (overflow is dropped). */
 int fizz_set_trace(FizzGroup *g, void *dev_records, int64_t capacity, void *dev_counter);
 
-/* Introspection for bench/roofline reporting. */
-int fizz_kernel_info(FizzGroup *g, int32_t *regs_per_thread, int32_t *smem_bytes_per_block, int32_t *block_threads,
-                     int32_t *blocks_per_sm, int64_t *launches);
+/* Introspection for bench/roofline reporting: `which` = FIZZ_KERNEL_*; launches = kernels launched so far. */
+int fizz_kernel_info(FizzGroup *g, int32_t which, int32_t *regs_per_thread, int32_t *smem_bytes_per_block,
+                     int32_t *block_threads, int32_t *blocks_per_sm, int64_t *launches);
+
+/* Optional per-kernel device timing (CUDA events on the launching stream, recorded inside fizz_step).
+ * fizz_profile_read synchronises on the recorded events and returns accumulated milliseconds and launch counts
+ * indexed by FIZZ_KERNEL_* (the work-list kernel is counted with the contact kernel). */
+int fizz_set_profiling(FizzGroup *g, int32_t enabled);
+int fizz_profile_read(FizzGroup *g, double *ms3, int64_t *launches3, int32_t reset);
 
 /* FP64 FMA throughput microbenchmark (the roofline denominator MEASURED_PEAKS.json lacks): runs `iters`
  * dependent-chain DFMA rounds on every SM of `device` and returns achieved TFLOP/s (FMA = 2 flops). */

@@ -287,7 +287,10 @@ class OracleWorld:
         return lib().fzo_total_ops(self._h)
 
     def contacts(self):
-        n = min(lib().fzo_contact_count(self._h), len(self._trace) if self._trace else 0)
+        n = lib().fzo_contact_count(self._h)
+        if n > (len(self._trace) if self._trace else 0):
+            raise OverflowError("oracle contact trace overflow: %d records, capacity %d"
+                                % (n, len(self._trace) if self._trace else 0))
         return [(c.step, c.call, c.i, c.j, c.nx, c.ny, c.mag) for c in self._trace[:n]]
 
     def dump(self):
