@@ -3,15 +3,20 @@
 // One WARP per world, persistent: warps pull world indices from a device-side work list (worlds the ballistic
 // kernel stopped at a non-empty broad phase, plus step 0 of every world).  The world's state (com, snapshot,
 // polar offsets, vertices, contact list) lives in the warp's slice of shared memory for the whole launch; the
-// fixed scene is staged once per CTA.  Each check_collisions() (physics.py:262-289) is executed cooperatively:
-//   * broad phase: lanes stride over the pair table, __ballot compacts the survivors in reference pair order;
-//   * narrow phase: lanes map to (pair, axis) items of polypoly_collision (:765-840) -- one SAT axis per lane,
-//     several pairs per 32-lane round -- followed by segmented __shfl reductions ("any separating axis",
-//     first strict minimum overlap in axis order) and a __ballot-compacted contact list;
+// fixed scene is staged once per CTA.  A pass over a batch is bounded by the SEQUENTIAL depth of its worst world
+// (30 halving trials + fallback + up to ~100 resolve passes per timestep for a trapped body), so
+// everything here is organised around the latency of one check_collisions() (physics.py:262-289):
+//   * broad phase: lanes stride over a packed pair table, __ballot compacts the survivors in reference order;
+//   * narrow phase: lanes map to (pair, axis) items of polypoly_collision (:765-840) in fixed-width slots, two
+//     items per lane for ILP, butterfly __shfl reductions inside a slot ("any separating axis", first strict
+//     minimum overlap in axis order), __ballot-compacted contact list;
+//   * the unit normal of a free polygon's edge, sqrt + 2 divisions (:790), is memoised on the exact edge vector:
+//     it is a pure function of (ax, ay) and >98% of evaluations repeat the previous bit pattern;
+//   * step halving (:99-129) is searched speculatively: once trial 0 fails, lane t evaluates trial t on its own
+//     (every trial restarts from the start-of-step state, so they are independent) and a __ballot picks the
+//     first trial that ends the loop;
 //   * resolution (:142-233) walks the list in order; vertices are pushed lane-parallel, the centre of mass by
 //     lane 0.
-// The sequential depth of a contact step (30 halving trials + fallback + N resolve passes) is
-// what bounds a pass over a batch; this kernel exists to make each of those rounds short.
 #pragma once
 
 #include "fizz_common.cuh"
@@ -22,23 +27,37 @@ constexpr int CONTACT_WARPS = 4;  // warps per CTA
 constexpr int CONTACT_BLOCK = CONTACT_WARPS * 32;
 constexpr int SP_CAP = 160;       // survivor list capacity (>= MAX_PAIRS)
 
+// packed pair descriptor: ii[0,4) jj[4,9) n1[9,14) n2[14,19) v1[19,27) v2[27,35)
+typedef unsigned long long pairmeta_t;
+__host__ __device__ __forceinline__ pairmeta_t pack_pair(int ii, int jj, int n1, int n2, int v1, int v2) {
+    return (pairmeta_t)ii | ((pairmeta_t)jj << 4) | ((pairmeta_t)n1 << 9) | ((pairmeta_t)n2 << 14) |
+           ((pairmeta_t)v1 << 19) | ((pairmeta_t)v2 << 27);
+}
+#define PM_II(m) ((int)((m) & 15))
+#define PM_JJ(m) ((int)(((m) >> 4) & 31))
+#define PM_N1(m) ((int)(((m) >> 9) & 31))
+#define PM_N2(m) ((int)(((m) >> 14) & 31))
+#define PM_V1(m) ((int)(((m) >> 19) & 255))
+#define PM_V2(m) ((int)(((m) >> 27) & 255))
+
 struct ContactSmem {
     // CTA-shared
     double *sfix, *fcx, *fcy, *fthr;
-    int *nv, *vs;
-    unsigned char *vbody, *pair_i, *pair_j;
+    pairmeta_t *pair_meta;
+    unsigned char *vbody;
     // per-warp
     double *px, *py, *vx, *vy, *sx, *sy, *thr, *mass, *npx, *npy, *off, *vert, *hnx, *hny, *hmag;
-    unsigned char *hi, *hj, *spi, *spj;
+    double *max_, *may_, *mnx, *mny;  // edge-normal memo per free vertex (edge v -> v+1)
+    pairmeta_t *sp;                   // surviving pairs of the last broad phase
+    unsigned char *hi, *hj;
 };
 
 __host__ __device__ inline size_t contact_smem_bytes(int V, int FV) {
-    size_t cta_d = (size_t)FV * 6 + 3 * FIZZ_MAX_FIXED;
-    size_t warp_d = 80 + 4 * (size_t)V + 96;
+    size_t cta_d = (size_t)FV * 6 + 3 * FIZZ_MAX_FIXED + SP_CAP;
+    size_t warp_d = 80 + 8 * (size_t)V + 96 + SP_CAP;
     size_t bytes = 8 * (cta_d + CONTACT_WARPS * warp_d);
-    bytes += 4 * 64;                                   // nv, vs
-    bytes += ((size_t)V + 15) / 16 * 16 + 2 * SP_CAP;  // vbody, pair tables
-    bytes += CONTACT_WARPS * (64 + 2 * SP_CAP);        // hi, hj, spi, spj
+    bytes += ((size_t)V + 15) / 16 * 16;  // vbody
+    bytes += CONTACT_WARPS * 64;          // hi, hj
     return (bytes + 15) / 16 * 16;
 }
 
@@ -49,52 +68,63 @@ __device__ __forceinline__ ContactSmem contact_carve(double *base, int V, int FV
     s.fcx = d; d += FIZZ_MAX_FIXED;
     s.fcy = d; d += FIZZ_MAX_FIXED;
     s.fthr = d; d += FIZZ_MAX_FIXED;
-    const int warp_d = 80 + 4 * V + 96;
+    s.pair_meta = reinterpret_cast<pairmeta_t *>(d); d += SP_CAP;
+    const int warp_d = 80 + 8 * V + 96 + SP_CAP;
     double *wd = d + (size_t)warp * warp_d;
     d += (size_t)CONTACT_WARPS * warp_d;
     s.px = wd; s.py = wd + 8; s.vx = wd + 16; s.vy = wd + 24; s.sx = wd + 32; s.sy = wd + 40;
     s.thr = wd + 48; s.mass = wd + 56; s.npx = wd + 64; s.npy = wd + 72;
     s.off = wd + 80; s.vert = s.off + 2 * V;
-    s.hnx = s.vert + 2 * V; s.hny = s.hnx + 32; s.hmag = s.hny + 32;
-    int *ip = reinterpret_cast<int *>(d);
-    s.nv = ip; s.vs = ip + 32;
-    unsigned char *b = reinterpret_cast<unsigned char *>(ip + 64);
+    s.max_ = s.vert + 2 * V; s.may_ = s.max_ + V; s.mnx = s.may_ + V; s.mny = s.mnx + V;
+    s.hnx = s.mny + V; s.hny = s.hnx + 32; s.hmag = s.hny + 32;
+    s.sp = reinterpret_cast<pairmeta_t *>(s.hmag + 32);
+    unsigned char *b = reinterpret_cast<unsigned char *>(d);
     s.vbody = b; b += (V + 15) / 16 * 16;
-    s.pair_i = b; b += SP_CAP;
-    s.pair_j = b; b += SP_CAP;
-    unsigned char *wb = b + (size_t)warp * (64 + 2 * SP_CAP);
-    s.hi = wb; s.hj = wb + 32; s.spi = wb + 64; s.spj = wb + 64 + SP_CAP;
+    unsigned char *wb = b + (size_t)warp * 64;
+    s.hi = wb; s.hj = wb + 32;
     return s;
 }
 
-// One SAT axis of polypoly_collision (:787-830) for pair (ii free, jj free-or-fixed): axis index k in
-// [0, n1+n2) in reference order (poly1's edges, then poly2's).  Returns the overlap on this axis (NaN-safe)
-// and whether the axis separates the polygons.
-__device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, int ii, int jj, int k, double &nx, double &ny,
+// Unit normal of the edge e -> e+1 of a free polygon whose vertices are (vx[e], vy[e]) (:775,:778,:790).
+// MEMO: read-write memo on the exact edge vector; pass false from code where several lanes may evaluate the same
+// edge with different vertex sets (speculative trials): then the memo is only read.
+template <bool MEMO_WRITE>
+__device__ __forceinline__ void edge_normal(const ContactSmem &s, int m, double x0, double y0, double x1, double y1,
+                                            double &nx, double &ny) {
+    const double ax = y1 - y0;   // (p2.y - p1.y, p1.x - p2.x)
+    const double ay = x0 - x1;
+    if (ax == s.max_[m] && ay == s.may_[m]) {
+        nx = s.mnx[m]; ny = s.mny[m];
+    } else {
+        const double nrm = sqrt(fma(ay, ay, ax * ax));  // :790
+        nx = ax / nrm; ny = ay / nrm;
+        if (MEMO_WRITE) { s.max_[m] = ax; s.may_[m] = ay; s.mnx[m] = nx; s.mny[m] = ny; }
+    }
+}
+
+// One SAT axis of polypoly_collision (:787-830) for the packed pair `m` (ii free, jj free-or-fixed): axis index
+// k in [0, n1+n2) in reference order (poly1's edges, then poly2's), vertices read from the warp's explicit
+// vertex array.  Returns the overlap on this axis and whether the axis separates the polygons.
+__device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, pairmeta_t m, int k, double &nx, double &ny,
                                          double &cur, bool &sep) {
-    const int n1 = s.nv[ii], v1 = s.vs[ii];
-    const int n2 = s.nv[jj], v2 = s.vs[jj];
+    const int jj = PM_JJ(m), n1 = PM_N1(m), n2 = PM_N2(m), v1 = PM_V1(m), v2 = PM_V2(m);
     const bool fx2 = jj >= F;
     const double *vert = s.vert;
     double lo2 = 0.0, hi2 = 0.0;
     bool own2 = false;
     if (k < n1) {
         const int k2 = (k + 1 == n1) ? 0 : k + 1;
-        const double ax = vert[2 * (v1 + k2) + 1] - vert[2 * (v1 + k) + 1];  // :775 (p2.y - p1.y, p1.x - p2.x)
-        const double ay = vert[2 * (v1 + k)] - vert[2 * (v1 + k2)];
-        const double nrm = sqrt(fma(ay, ay, ax * ax));                       // :790
-        nx = ax / nrm; ny = ay / nrm;
+        edge_normal<true>(s, v1 + k, vert[2 * (v1 + k)], vert[2 * (v1 + k) + 1], vert[2 * (v1 + k2)],
+                          vert[2 * (v1 + k2) + 1], nx, ny);
     } else if (fx2) {
-        const double *g = s.sfix + (v2 + (k - n1)) * 6;                      // precomputed, bit-identical to :778,:790
+        const double *g = s.sfix + (v2 + (k - n1)) * 6;  // precomputed, bit-identical to :778,:790,:806-811
         nx = g[2]; ny = g[3]; lo2 = g[4]; hi2 = g[5];
         own2 = true;
     } else {
         const int e = k - n1;
         const int e2 = (e + 1 == n2) ? 0 : e + 1;
-        const double ax = vert[2 * (v2 + e2) + 1] - vert[2 * (v2 + e) + 1];  // :778
-        const double ay = vert[2 * (v2 + e)] - vert[2 * (v2 + e2)];
-        const double nrm = sqrt(fma(ay, ay, ax * ax));
-        nx = ax / nrm; ny = ay / nrm;
+        edge_normal<true>(s, v2 + e, vert[2 * (v2 + e)], vert[2 * (v2 + e) + 1], vert[2 * (v2 + e2)],
+                          vert[2 * (v2 + e2) + 1], nx, ny);
     }
     double lo1, hi1;
     lo1 = hi1 = dot2(nx, ny, vert[2 * v1], vert[2 * v1 + 1]);                // :795
@@ -129,6 +159,69 @@ __device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, int ii, in
     cur = hi1 - lo2;                                                         // :824
 }
 
+// Whole polypoly_collision for one pair evaluated by ONE lane with the free vertices rebuilt on the fly from a
+// trial's moved centres of mass (speculative halving).  Returns true and |overlap| when the pair collides.
+__device__ __forceinline__ bool sat_pair_trial(const ContactSmem &s, int F, pairmeta_t m, double c1x, double c1y,
+                                               double c2x, double c2y, double &mag) {
+    const int jj = PM_JJ(m), n1 = PM_N1(m), n2 = PM_N2(m), v1 = PM_V1(m), v2 = PM_V2(m);
+    const bool fx2 = jj >= F;
+    const double *off = s.off;
+    double overlap = INFINITY;
+    bool have = false;
+    for (int k = 0; k < n1 + n2; k++) {
+        double nx, ny, lo2 = 0.0, hi2 = 0.0;
+        bool own2 = false;
+        if (k < n1) {
+            const int k2 = (k + 1 == n1) ? 0 : k + 1;
+            edge_normal<false>(s, v1 + k, off[2 * (v1 + k)] + c1x, off[2 * (v1 + k) + 1] + c1y, off[2 * (v1 + k2)] + c1x,
+                               off[2 * (v1 + k2) + 1] + c1y, nx, ny);
+        } else if (fx2) {
+            const double *g = s.sfix + (v2 + (k - n1)) * 6;
+            nx = g[2]; ny = g[3]; lo2 = g[4]; hi2 = g[5];
+            own2 = true;
+        } else {
+            const int e = k - n1;
+            const int e2 = (e + 1 == n2) ? 0 : e + 1;
+            edge_normal<false>(s, v2 + e, off[2 * (v2 + e)] + c2x, off[2 * (v2 + e) + 1] + c2y, off[2 * (v2 + e2)] + c2x,
+                               off[2 * (v2 + e2) + 1] + c2y, nx, ny);
+        }
+        double lo1, hi1;
+        lo1 = hi1 = dot2(nx, ny, off[2 * v1] + c1x, off[2 * v1 + 1] + c1y);
+        for (int v = 1; v < n1; v++) {
+            const double c = dot2(nx, ny, off[2 * (v1 + v)] + c1x, off[2 * (v1 + v) + 1] + c1y);
+            if (c < lo1) lo1 = c;
+            if (c > hi1) hi1 = c;
+        }
+        if (!own2) {
+            if (fx2) {
+                const double *g = s.sfix + v2 * 6;
+                lo2 = hi2 = dot2(nx, ny, g[0], g[1]);
+                for (int v = 1; v < n2; v++) {
+                    const double c = dot2(nx, ny, g[v * 6], g[v * 6 + 1]);
+                    if (c < lo2) lo2 = c;
+                    if (c > hi2) hi2 = c;
+                }
+            } else {
+                lo2 = hi2 = dot2(nx, ny, off[2 * v2] + c2x, off[2 * v2 + 1] + c2y);
+                for (int v = 1; v < n2; v++) {
+                    const double c = dot2(nx, ny, off[2 * (v2 + v)] + c2x, off[2 * (v2 + v) + 1] + c2y);
+                    if (c < lo2) lo2 = c;
+                    if (c > hi2) hi2 = c;
+                }
+            }
+        }
+        if (lo1 > lo2) {
+            double t = lo1; lo1 = lo2; lo2 = t;
+            t = hi1; hi1 = hi2; hi2 = t;
+        }
+        if (hi1 < lo2) return false;
+        const double cur = hi1 - lo2;
+        if (cur < overlap) { overlap = cur; have = true; }
+    }
+    mag = fabs(overlap);
+    return have;
+}
+
 __global__ void __launch_bounds__(CONTACT_BLOCK, 4)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
                const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor) {
@@ -143,18 +236,29 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
     // ---- stage the scene once per CTA ----------------------------------------------------------------------
     for (int i = tid; i < kp.FV * 6; i += CONTACT_BLOCK) s.sfix[i] = kp.fixed_geom[i];
     if (tid < FIZZ_MAX_FIXED) { s.fcx[tid] = kp.fcx[tid]; s.fcy[tid] = kp.fcy[tid]; s.fthr[tid] = kp.fthr[tid]; }
-    if (tid < F + X) { s.nv[tid] = kp.nv[tid]; s.vs[tid] = kp.vs[tid]; }
     if (tid == 0) {
         int p = 0;
         for (int i = 0; i < F; i++)
-            for (int j = i + 1; j < F + X; j++) { s.pair_i[p] = (unsigned char)i; s.pair_j[p] = (unsigned char)j; p++; }
+            for (int j = i + 1; j < F + X; j++)
+                s.pair_meta[p++] = pack_pair(i, j, kp.nv[i], kp.nv[j], kp.vs[i], kp.vs[j]);
         for (int b = 0; b < F; b++)
             for (int v = 0; v < kp.nv[b]; v++) s.vbody[kp.vs[b] + v] = (unsigned char)b;
     }
     __syncthreads();
 
+    // slot width of the narrow phase: smallest power of two >= the largest n1+n2 of the scene
+    int max_na = 0;
+    for (int i = 0; i < F; i++)
+        for (int j = i + 1; j < F + X; j++) max_na = max(max_na, kp.nv[i] + kp.nv[j]);
+    const int SW = max_na <= 8 ? 8 : (max_na <= 16 ? 16 : 32);
+    const int SWL = max_na <= 8 ? 3 : (max_na <= 16 ? 4 : 5);
+    const int PR = 32 >> SWL;                    // pairs per 32-lane set
+    const int my_slot = lane >> SWL, my_k = lane & (SW - 1);
+    const unsigned slot_mask = (SW == 32 ? FULL : ((1u << SW) - 1u)) << (my_slot * SW);
+
     const long long Wp = kp.Wp;
     const unsigned long long count = *count_ptr;
+    const bool speculate = (kp.trace == nullptr);  // the contact trace needs every trial's tuples: sequential then
 
     for (;;) {
         unsigned long long idx = 0;
@@ -173,6 +277,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             s.mass[lane] = kp.mass[lane * Wp + w];
         }
         for (int r = lane; r < 2 * V; r += 32) s.off[r] = kp.off[(size_t)r * Wp + w];
+        for (int v = lane; v < V; v += 32) s.max_[v] = NAN;  // empty memo: NaN never compares equal
         double heat = kp.heat[w];
         long long step = kp.steps[w];
         long long status = 0;
@@ -209,9 +314,10 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 for (int p0 = 0; p0 < P; p0 += 32) {
                     const int p = p0 + lane;
                     bool surv = false;
-                    int i = 0, j = 0;
+                    pairmeta_t m = 0;
                     if (p < P) {
-                        i = s.pair_i[p]; j = s.pair_j[p];
+                        m = s.pair_meta[p];
+                        const int i = PM_II(m), j = PM_JJ(m);
                         double ox, oy, ot;
                         if (j < F) { ox = s.sx[j]; oy = s.sy[j]; ot = s.thr[j]; }
                         else { ox = s.fcx[j - F]; oy = s.fcy[j - F]; ot = s.fthr[j - F]; }
@@ -220,10 +326,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         surv = !(d2 > s.thr[i] && d2 > ot);
                     }
                     const unsigned b = __ballot_sync(FULL, surv);
-                    if (surv) {
-                        const int slot = ns + __popc(b & lt_mask);
-                        s.spi[slot] = (unsigned char)i; s.spj[slot] = (unsigned char)j;
-                    }
+                    if (surv) s.sp[ns + __popc(b & lt_mask)] = m;
                     ns += __popc(b);
                 }
                 __syncwarp();
@@ -243,62 +346,66 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     }
                     __syncwarp();
                 }
-                // ---- narrow phase: (pair, axis) items, several pairs per 32-lane round --------------------------
-                int p0 = 0;
-                while (p0 < ns) {
-                    int acc = 0, p = p0, myp = -1, myk = 0, seg0 = 0, segn = 1;
-                    while (p < ns) {
-                        const int na = s.nv[s.spi[p]] + s.nv[s.spj[p]];
-                        if (acc + na > 32) break;
-                        if (lane >= acc && lane < acc + na) { myp = p; myk = lane - acc; seg0 = acc; segn = na; }
-                        acc += na;
-                        p++;
+                // ---- narrow phase: (pair, axis) items in SW-wide slots, two sets of PR pairs per round ------------
+                for (int p0 = 0; p0 < ns; p0 += 2 * PR) {
+                    const int pa = p0 + my_slot, pb = p0 + PR + my_slot;
+                    pairmeta_t ma = 0, mb = 0;
+                    double nxa = 0.0, nya = 0.0, cura = INFINITY, nxb = 0.0, nyb = 0.0, curb = INFINITY;
+                    bool sepa = false, sepb = false, acta = false, actb = false;
+                    if (pa < ns) {
+                        ma = s.sp[pa];
+                        acta = my_k < PM_N1(ma) + PM_N2(ma);
                     }
-                    double nx = 0.0, ny = 0.0, cur = INFINITY;
-                    bool sep = false;
-                    int ii = 0, jj = 0;
-                    if (myp >= 0) {
-                        ii = s.spi[myp]; jj = s.spj[myp];
-                        sat_axis(s, F, ii, jj, myk, nx, ny, cur, sep);
+                    if (pb < ns) {
+                        mb = s.sp[pb];
+                        actb = my_k < PM_N1(mb) + PM_N2(mb);
                     }
-                    const unsigned sepb = __ballot_sync(FULL, sep);
-                    const unsigned segmask = (segn >= 32 ? FULL : ((1u << segn) - 1u)) << seg0;
-                    const bool pair_sep = (sepb & segmask) != 0;
-                    // first strict minimum in axis order (:827-830) = lexicographic min of (overlap, axis)
-                    const bool valid = (myp >= 0) && (cur < INFINITY);
-                    double bov = valid ? cur : INFINITY;
-                    int bk = valid ? myk : 99;
+                    if (acta) sat_axis(s, F, ma, my_k, nxa, nya, cura, sepa);
+                    if (actb) sat_axis(s, F, mb, my_k, nxb, nyb, curb, sepb);
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double oov = __shfl_down_sync(FULL, bov, o);
-                        const int ok = __shfl_down_sync(FULL, bk, o);
-                        if (myp >= 0 && lane + o < seg0 + segn) {
+                    for (int set = 0; set < 2; set++) {
+                        const pairmeta_t m = set ? mb : ma;
+                        const bool act = set ? actb : acta, sep = set ? sepb : sepa;
+                        const double nx = set ? nxb : nxa, ny = set ? nyb : nya, cur = set ? curb : cura;
+                        const bool pair_live = (set ? pb : pa) < ns;
+                        if (set == 1 && p0 + PR >= ns) break;  // uniform
+                        const unsigned sepbits = __ballot_sync(FULL, sep);
+                        const bool pair_sep = (sepbits & slot_mask) != 0;
+                        // first strict minimum in axis order (:827-830) = lexicographic min of (overlap, axis)
+                        const bool valid = act && (cur < INFINITY);
+                        double bov = valid ? cur : INFINITY;
+                        int bk = valid ? my_k : 99;
+                        for (int o = 1; o < SW; o <<= 1) {
+                            const double oov = __shfl_xor_sync(FULL, bov, o);
+                            const int ok = __shfl_xor_sync(FULL, bk, o);
                             if (oov < bov || (oov == bov && ok < bk)) { bov = oov; bk = ok; }
                         }
-                    }
-                    const int src = (seg0 + (bk == 99 ? 0 : bk)) & 31;
-                    const double fxn = __shfl_sync(FULL, nx, src), fyn = __shfl_sync(FULL, ny, src);
-                    const bool hit = (myp >= 0) && (lane == seg0) && !pair_sep && (bk != 99);  // :286-288
-                    const unsigned hitb = __ballot_sync(FULL, hit);
-                    double am = -1.0;
-                    if (hit) {
-                        const int slot = nh + __popc(hitb & lt_mask);
-                        const double hx = fxn * -1.0, hy = fyn * -1.0;  // :838-839 always negated (Q7)
-                        if (slot < FIZZ_MAX_HITS) {
-                            s.hi[slot] = (unsigned char)ii; s.hj[slot] = (unsigned char)jj;
-                            s.hnx[slot] = hx; s.hny[slot] = hy; s.hmag[slot] = bov;
+                        const int src = (my_slot * SW + (bk == 99 ? 0 : bk)) & 31;
+                        const double fxn = __shfl_sync(FULL, nx, src), fyn = __shfl_sync(FULL, ny, src);
+                        const bool hit = pair_live && (my_k == 0) && !pair_sep && (bk != 99);  // :286-288
+                        const unsigned hitb = __ballot_sync(FULL, hit);
+                        if (hitb) {
+                            if (hit) {
+                                const int slot = nh + __popc(hitb & lt_mask);
+                                const double hx = fxn * -1.0, hy = fyn * -1.0;  // :838-839 always negated (Q7)
+                                const int ii = PM_II(m), jj = PM_JJ(m);
+                                if (slot < FIZZ_MAX_HITS) {
+                                    s.hi[slot] = (unsigned char)ii; s.hj[slot] = (unsigned char)jj;
+                                    s.hnx[slot] = hx; s.hny[slot] = hy; s.hmag[slot] = bov;
+                                }
+                                if (kp.trace) trace_hit(kp, w, step, ncalls, ii, jj, hx, hy, bov);
+                            }
+                            nh += __popc(hitb);
+                            // max |overlap| over this set's hits: slot leaders hold them
+                            double am = hit ? fabs(bov) : -1.0;
+                            for (int o = SW; o < 32; o <<= 1) {
+                                const double other = __shfl_xor_sync(FULL, am, o);
+                                if (other > am) am = other;
+                            }
+                            am = __shfl_sync(FULL, am, 0);
+                            if (am > maxov) maxov = am;
                         }
-                        am = fabs(bov);
-                        if (kp.trace) trace_hit(kp, w, step, ncalls, ii, jj, hx, hy, bov);
                     }
-                    nh += __popc(hitb);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double other = __shfl_xor_sync(FULL, am, o);
-                        if (other > am) am = other;
-                    }
-                    if (am > maxov) maxov = am;
-                    p0 = p;
                 }
                 __syncwarp();
                 if (nh > FIZZ_MAX_HITS) { status = FIZZ_ST_HIT_OVERFLOW; break; }
@@ -306,6 +413,45 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 
             if (!resolve) {
                 if (maxov > kp.coll_tol && dt > kp.time_tol) {  // :99
+                    if (k == 0 && speculate) {
+                        // ---- speculative halving: lane t evaluates trial t (dt / 2^t) on its own -----------------
+                        double dtt = dt;
+                        for (int t = 0; t < lane; t++) dtt = dtt / 2;   // exact, like the repeated :106
+                        bool done_t = true;                              // "this trial ends the :99 loop"
+                        // trials exist while the previous one still had dt > time_tol; lane t >= 1 is a real trial iff
+                        // dt_{t-1} > time_tol, which is monotone, so the first `done` lane below is always real
+                        if (lane >= 1) {
+                            double mo = 0.0;
+                            for (int p = 0; p < ns; p++) {
+                                const pairmeta_t m = s.sp[p];
+                                const int ii = PM_II(m), jj = PM_JJ(m);
+                                double c1x, c1y, c2x = 0.0, c2y = 0.0;
+                                [[maybe_unused]] double dvx, dvy;
+                                FIZZ_MOVE_POINT(s.px[ii], s.py[ii], s.vx[ii], s.vy[ii], dtt, a0x, a0y, kp.accx, kp.accy, c1x,
+                                                c1y, dvx, dvy);
+                                if (jj < F) {
+                                    FIZZ_MOVE_POINT(s.px[jj], s.py[jj], s.vx[jj], s.vy[jj], dtt, a0x, a0y, kp.accx, kp.accy,
+                                                    c2x, c2y, dvx, dvy);
+                                }
+                                double mag;
+                                if (sat_pair_trial(s, F, m, c1x, c1y, c2x, c2y, mag))
+                                    if (mag > mo) mo = mag;
+                            }
+                            done_t = !(mo > kp.coll_tol && dtt > kp.time_tol);
+                        } else {
+                            done_t = false;  // trial 0 is the one that just failed
+                        }
+                        const unsigned doneb = __ballot_sync(FULL, done_t);
+                        const int kstar = __ffs(doneb) - 1;  // >= 1: dt_31 < time_tol for any sane time_tol
+                        if (kstar >= 1) {
+                            // trials 1 .. kstar-1 were made (and failed); trial kstar is run for real next round
+                            ncalls += kstar - 1;
+                            ncalls_total += kstar - 1;
+                            k = kstar;
+                            dt = __shfl_sync(FULL, dtt, kstar);
+                            continue;
+                        }
+                    }
                     dt = dt / 2;                                // :106
                     k++;
                     continue;
@@ -331,10 +477,10 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     const double ux = s.hnx[h], uy = s.hny[h];
                     const double sc = s.hmag[h] + kp.eps;      // :158
                     const double nvx = ux * sc, nvy = uy * sc;
-                    const int n1 = s.nv[ii], v1 = s.vs[ii];
+                    const int n1 = kp.nv[ii], v1 = kp.vs[ii];
                     if (jj >= F) {                             // :171-198 free body vs fixed body
                         if (lane < n1) { s.vert[2 * (v1 + lane)] += nvx; s.vert[2 * (v1 + lane) + 1] += nvy; }  // :174
-                        const bool gate = sqrt(fma(nvy, nvy, nvx * nvx)) > kp.vib_tol;  // :180
+                        const bool gate = fma(nvy, nvy, nvx * nvx) > kp.vib_thr;  // :180 norm(nv) > VIBRATE_TOL
                         double cpx = s.px[ii], cpy = s.py[ii], cvx = s.vx[ii], cvy = s.vy[ii];
                         const double m1 = s.mass[ii];
                         if (gate) { cpx += nvx; cpy += nvy; }                           // :181
@@ -349,7 +495,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                             s.sx[ii] = cpx; s.sy[ii] = cpy;                             // :197
                         }
                     } else {                                   // :201-223 two free bodies
-                        const int n2 = s.nv[jj], v2 = s.vs[jj];
+                        const int n2 = kp.nv[jj], v2 = kp.vs[jj];
                         const double m1 = s.mass[ii], m2 = s.mass[jj];
                         const double mtotal = m1 + m2;
                         const double mprop1 = m1 / mtotal;

@@ -304,6 +304,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     kp.coll_tol = p.collision_tol; kp.time_tol = p.time_tol; kp.eps = p.epsilon; kp.vib_tol = p.vibrate_tol;
     kp.time_disc = p.time_disc; kp.ope = p.one_plus_e; kp.ome2 = p.one_minus_e2; kp.accx = p.acc_x; kp.accy = p.acc_y;
     kp.max_calls = p.max_calls;
+    fizz_host_sqrt_threshold(1, &p.vibrate_tol, &kp.vib_thr);
 
     // thread mode (may not fit in shared memory for vertex-rich worlds: then only hybrid mode is available)
     g->thread_smem = sizeof(double) * ((size_t)kp.FV * 6 + (size_t)kp.V * 2 * BLOCK) + sizeof(int) * 64;
