@@ -93,7 +93,9 @@ __device__ __forceinline__ void edge_normal(const ContactSmem &s, int m, double 
                                             double &nx, double &ny) {
     const double ax = y1 - y0;   // (p2.y - p1.y, p1.x - p2.x)
     const double ay = x0 - x1;
-    if (ax == s.max_[m] && ay == s.may_[m]) {
+    // bitwise key: -0.0 and +0.0 give normals that differ in the sign of zero
+    if (__double_as_longlong(ax) == __double_as_longlong(s.max_[m]) &&
+        __double_as_longlong(ay) == __double_as_longlong(s.may_[m])) {
         nx = s.mnx[m]; ny = s.mny[m];
     } else {
         const double nrm = sqrt(fma(ay, ay, ax * ax));  // :790
@@ -222,7 +224,179 @@ __device__ __forceinline__ bool sat_pair_trial(const ContactSmem &s, int F, pair
     return have;
 }
 
-__global__ void __launch_bounds__(CONTACT_BLOCK, 4)
+// ---------------------------------------------------------------------------------------------------------------
+// Single-contact resolve fast path.
+//
+// The worlds that bound a pass are a free polygon b trapped against FIXED polygons: every check_collisions() of
+// the resolve loop (:140-234) returns exactly one tuple (b, fixed j) for hundreds of passes per timestep.  Between
+// two such passes only b changes, so (1) every pair without b keeps its result ("no contact"), (2) only the pairs
+// (b, *) need the broad phase again, and as long as the same fixed partners (and no free body) pass it, (3) the
+// SAT work is a fixed set of (partner, axis) items.  This loop keeps b's vertices, the lane's axis constants, its
+// edge-normal memo and the partner's projection bounds in REGISTERS and runs check_collisions() + resolution
+// back to back; it returns to the general path -- with the state written back exactly as it is right before the
+// check_collisions() call at :234 -- as soon as anything else happens (other candidate set, zero or several
+// tuples, watchdog).  Arithmetic is the same, operation for operation, as the general path.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NM>
+__device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
+                                             double &heat, int &ncalls, long long &ncalls_total) {
+    const unsigned FULL = 0xffffffffu;
+    const int n1 = kp.nv[b], v1 = kp.vs[b];
+    double cpx = s.px[b], cpy = s.py[b], cvx = s.vx[b], cvy = s.vy[b];
+    const double m1 = s.mass[b], thr_b = s.thr[b];
+    double vtx[NM], vty[NM];
+#pragma unroll
+    for (int v = 0; v < NM; v++) {
+        vtx[v] = (v < n1) ? s.vert[2 * (v1 + v)] : 0.0;
+        vty[v] = (v < n1) ? s.vert[2 * (v1 + v) + 1] : 0.0;
+    }
+    // this lane's broad-phase partner: body `lane` of objs+fixed_objs
+    const bool partner = (lane < F + X) && (lane != b);
+    double ox = 0.0, oy = 0.0, ot = 0.0;
+    if (partner) {
+        if (lane < F) { ox = s.sx[lane]; oy = s.sy[lane]; ot = s.thr[lane]; }
+        else { ox = s.fcx[lane - F]; oy = s.fcy[lane - F]; ot = s.fthr[lane - F]; }
+    }
+    bool surv = false;
+    if (partner) {
+        // pairs are ordered (i < j): the snapshot of the lower index is the minuend (:277)
+        const double dx = (lane < b) ? ox - cpx : cpx - ox, dy = (lane < b) ? oy - cpy : cpy - oy;
+        const double d2 = fma(dy, dy, dx * dx);
+        surv = !(d2 > thr_b && d2 > ot);
+    }
+    const unsigned mask0 = __ballot_sync(FULL, surv);
+    const int ncand = __popc(mask0);
+    if (ncand == 0 || ncand > 4 || (mask0 & ((1u << F) - 1u)) != 0) return;  // only fixed partners, one 32-lane set
+
+    const int slot = lane >> 3, k = lane & 7;
+    int jj = -1;
+    {
+        unsigned mm = mask0;
+        for (int q = 0; q < slot; q++) mm &= mm - 1;
+        if (slot < ncand) jj = __ffs(mm) - 1;
+    }
+    int n2 = 0, v2 = 0;
+    if (jj >= 0) { n2 = kp.nv[jj]; v2 = kp.vs[jj]; }
+    const bool active = (jj >= 0) && (k < n1 + n2);
+    const bool freeaxis = active && (k < n1);
+    const unsigned slot_mask = 0xffu << (slot * 8);
+    // lane constants / lane-private memo
+    double cnx = 0.0, cny = 0.0, clo2 = 0.0, chi2 = 0.0;                       // fixed axis of the partner
+    double ex0 = 0.0, ey0 = 0.0, ex1 = 0.0, ey1 = 0.0;                           // this lane's edge of b
+    double mmax = NAN, mmay = NAN, mnx = 0.0, mny = 0.0;                         // edge-normal memo
+    double kx = NAN, ky = NAN, flo2 = 0.0, fhi2 = 0.0;                           // partner bounds on that normal
+    if (freeaxis) {
+        const int k2 = (k + 1 == n1) ? 0 : k + 1;
+        ex0 = s.vert[2 * (v1 + k)]; ey0 = s.vert[2 * (v1 + k) + 1];
+        ex1 = s.vert[2 * (v1 + k2)]; ey1 = s.vert[2 * (v1 + k2) + 1];
+        mmax = s.max_[v1 + k]; mmay = s.may_[v1 + k]; mnx = s.mnx[v1 + k]; mny = s.mny[v1 + k];
+    } else if (active) {
+        const double *g = s.sfix + (v2 + (k - n1)) * 6;
+        cnx = g[2]; cny = g[3]; clo2 = g[4]; chi2 = g[5];
+    }
+
+    for (;;) {
+        if (ncalls >= kp.max_calls) break;  // watchdog: the general path raises FIZZ_ST_CAPPED
+        // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
+        surv = false;
+        if (partner) {
+            const double dx = (lane < b) ? ox - cpx : cpx - ox, dy = (lane < b) ? oy - cpy : cpy - oy;
+            const double d2 = fma(dy, dy, dx * dx);
+            surv = !(d2 > thr_b && d2 > ot);
+        }
+        if (__ballot_sync(FULL, surv) != mask0) break;
+        // ---- narrow phase: one (partner, axis) item per lane ----------------------------------------------------
+        double nx = 0.0, ny = 0.0, cur = INFINITY;
+        bool sep = false;
+        if (active) {
+            double lo2, hi2;
+            if (freeaxis) {
+                const double ax = ey1 - ey0, ay = ex0 - ex1;
+                if (!(__double_as_longlong(ax) == __double_as_longlong(mmax) &&
+                      __double_as_longlong(ay) == __double_as_longlong(mmay))) {
+                    const double nrm = sqrt(fma(ay, ay, ax * ax));
+                    mnx = ax / nrm; mny = ay / nrm; mmax = ax; mmay = ay;
+                }
+                nx = mnx; ny = mny;
+                if (!(__double_as_longlong(nx) == __double_as_longlong(kx) &&
+                      __double_as_longlong(ny) == __double_as_longlong(ky))) {
+                    const double *g = s.sfix + v2 * 6;
+                    flo2 = fhi2 = dot2(nx, ny, g[0], g[1]);
+                    for (int v = 1; v < n2; v++) {
+                        const double c = dot2(nx, ny, g[v * 6], g[v * 6 + 1]);
+                        if (c < flo2) flo2 = c;
+                        if (c > fhi2) fhi2 = c;
+                    }
+                    kx = nx; ky = ny;
+                }
+                lo2 = flo2; hi2 = fhi2;
+            } else {
+                nx = cnx; ny = cny; lo2 = clo2; hi2 = chi2;
+            }
+            double lo1, hi1;
+            lo1 = hi1 = dot2(nx, ny, vtx[0], vty[0]);
+#pragma unroll
+            for (int v = 1; v < NM; v++) {
+                if (v < n1) {
+                    const double c = dot2(nx, ny, vtx[v], vty[v]);
+                    if (c < lo1) lo1 = c;
+                    if (c > hi1) hi1 = c;
+                }
+            }
+            if (lo1 > lo2) {
+                double t = lo1; lo1 = lo2; lo2 = t;
+                t = hi1; hi1 = hi2; hi2 = t;
+            }
+            sep = hi1 < lo2;
+            cur = hi1 - lo2;
+        }
+        const unsigned sepbits = __ballot_sync(FULL, sep);
+        const bool pair_sep = (sepbits & slot_mask) != 0;
+        const bool valid = active && (cur < INFINITY);
+        double bov = valid ? cur : INFINITY;
+        int bk = valid ? k : 99;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const double oov = __shfl_xor_sync(FULL, bov, o);
+            const int ok = __shfl_xor_sync(FULL, bk, o);
+            if (oov < bov || (oov == bov && ok < bk)) { bov = oov; bk = ok; }
+        }
+        const bool hit = (jj >= 0) && (k == 0) && !pair_sep && (bk != 99);
+        const unsigned hitb = __ballot_sync(FULL, hit);
+        if (__popc(hitb) != 1) break;  // zero tuples: the resolve loop ends; several: general path
+        const int hl = __ffs(hitb) - 1;                       // leader lane of the colliding partner's slot
+        const int wk = __shfl_sync(FULL, bk, hl);
+        const double mag = __shfl_sync(FULL, bov, hl);
+        const double ux = __shfl_sync(FULL, nx, hl + wk) * -1.0, uy = __shfl_sync(FULL, ny, hl + wk) * -1.0;
+        ncalls++;
+        ncalls_total++;
+        // ---- resolution, free body vs fixed body (:171-198) -----------------------------------------------------
+        const double sc = mag + kp.eps;
+        const double nvx = ux * sc, nvy = uy * sc;
+#pragma unroll
+        for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }
+        ex0 += nvx; ey0 += nvy; ex1 += nvx; ey1 += nvy;
+        if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }
+        const double vdotN = dot2(cvx, cvy, ux, uy);
+        const double cc = kp.ope * vdotN;
+        cvx -= cc * ux;
+        cvy -= cc * uy;
+        heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);
+    }
+    // ---- write the state back for the general path ----------------------------------------------------------------
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < NM; v++)
+        if (lane == v && v < n1) { s.vert[2 * (v1 + v)] = vtx[v]; s.vert[2 * (v1 + v) + 1] = vty[v]; }
+    if (freeaxis && slot == 0) { s.max_[v1 + k] = mmax; s.may_[v1 + k] = mmay; s.mnx[v1 + k] = mnx; s.mny[v1 + k] = mny; }
+    if (lane == 0) {
+        s.px[b] = cpx; s.py[b] = cpy; s.vx[b] = cvx; s.vy[b] = cvy; s.sx[b] = cpx; s.sy[b] = cpy;
+    }
+    __syncwarp();
+}
+
+
+__global__ void __launch_bounds__(CONTACT_BLOCK, 3)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
                const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor) {
     extern __shared__ double smem_c[];
@@ -522,6 +696,11 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     __syncwarp();
                 }
                 resolve = true;  // next round: check_collisions() at :234
+                if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F) {
+                    const int b = s.hi[0];
+                    if (kp.nv[b] <= 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                    else if (kp.nv[b] <= 8) fast_resolve<8>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                }
                 continue;
             }
 
