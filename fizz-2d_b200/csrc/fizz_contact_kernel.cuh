@@ -237,11 +237,13 @@ __device__ __forceinline__ bool sat_pair_trial(const ContactSmem &s, int F, pair
 // check_collisions() call at :234 -- as soon as anything else happens (other candidate set, zero or several
 // tuples, watchdog).  Arithmetic is the same, operation for operation, as the general path.
 // ---------------------------------------------------------------------------------------------------------------
-template <int NM>
+template <int N1>  // N1 = exact vertex count of b (3 or 4), or 0 = generic (<= 8 vertices, runtime count)
 __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
                                              double &heat, int &ncalls, long long &ncalls_total) {
+    constexpr int NM = N1 ? N1 : 8;
     const unsigned FULL = 0xffffffffu;
-    const int n1 = kp.nv[b], v1 = kp.vs[b];
+    const int n1 = N1 ? N1 : kp.nv[b];
+    const int v1 = kp.vs[b];
     double cpx = s.px[b], cpy = s.py[b], cvx = s.vx[b], cvy = s.vy[b];
     const double m1 = s.mass[b], thr_b = s.thr[b];
     double vtx[NM], vty[NM];
@@ -250,7 +252,8 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         vtx[v] = (v < n1) ? s.vert[2 * (v1 + v)] : 0.0;
         vty[v] = (v < n1) ? s.vert[2 * (v1 + v) + 1] : 0.0;
     }
-    // this lane's broad-phase partner: body `lane` of objs+fixed_objs
+    // this lane's broad-phase partner: body `lane` of objs+fixed_objs.  (a-b)^2 == (b-a)^2 exactly, so the order of
+    // the subtraction at :277 does not matter.
     const bool partner = (lane < F + X) && (lane != b);
     double ox = 0.0, oy = 0.0, ot = 0.0;
     if (partner) {
@@ -258,11 +261,10 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         else { ox = s.fcx[lane - F]; oy = s.fcy[lane - F]; ot = s.fthr[lane - F]; }
     }
     bool surv = false;
-    if (partner) {
-        // pairs are ordered (i < j): the snapshot of the lower index is the minuend (:277)
-        const double dx = (lane < b) ? ox - cpx : cpx - ox, dy = (lane < b) ? oy - cpy : cpy - oy;
+    {
+        const double dx = cpx - ox, dy = cpy - oy;
         const double d2 = fma(dy, dy, dx * dx);
-        surv = !(d2 > thr_b && d2 > ot);
+        surv = partner && !(d2 > thr_b && d2 > ot);
     }
     const unsigned mask0 = __ballot_sync(FULL, surv);
     const int ncand = __popc(mask0);
@@ -279,122 +281,118 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     if (jj >= 0) { n2 = kp.nv[jj]; v2 = kp.vs[jj]; }
     const bool active = (jj >= 0) && (k < n1 + n2);
     const bool freeaxis = active && (k < n1);
-    const unsigned slot_mask = 0xffu << (slot * 8);
-    // lane constants / lane-private memo
-    double cnx = 0.0, cny = 0.0, clo2 = 0.0, chi2 = 0.0;                       // fixed axis of the partner
-    double ex0 = 0.0, ey0 = 0.0, ex1 = 0.0, ey1 = 0.0;                           // this lane's edge of b
-    double mmax = NAN, mmay = NAN, mnx = 0.0, mny = 0.0;                         // edge-normal memo
-    double kx = NAN, ky = NAN, flo2 = 0.0, fhi2 = 0.0;                           // partner bounds on that normal
+    const unsigned live_all = (ncand >= 4) ? 0xfu : ((1u << ncand) - 1u);
+    // axis registers of this lane: unit normal, the partner's projection bounds on it, and -- for an edge of b -- the
+    // edge end points plus the exact edge vector the normal was computed from (memo key; NaN = not computed yet).
+    double anx = 0.0, any_ = 0.0, alo2 = 0.0, ahi2 = 0.0;
+    double ex0 = 0.0, ey0 = 0.0, ex1 = 0.0, ey1 = 0.0, keyx = 0.0, keyy = 0.0;
     if (freeaxis) {
         const int k2 = (k + 1 == n1) ? 0 : k + 1;
         ex0 = s.vert[2 * (v1 + k)]; ey0 = s.vert[2 * (v1 + k) + 1];
         ex1 = s.vert[2 * (v1 + k2)]; ey1 = s.vert[2 * (v1 + k2) + 1];
-        mmax = s.max_[v1 + k]; mmay = s.may_[v1 + k]; mnx = s.mnx[v1 + k]; mny = s.mny[v1 + k];
+        keyx = NAN; keyy = NAN;
     } else if (active) {
         const double *g = s.sfix + (v2 + (k - n1)) * 6;
-        cnx = g[2]; cny = g[3]; clo2 = g[4]; chi2 = g[5];
+        anx = g[2]; any_ = g[3]; alo2 = g[4]; ahi2 = g[5];
     }
 
     for (;;) {
         if (ncalls >= kp.max_calls) break;  // watchdog: the general path raises FIZZ_ST_CAPPED
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
-        surv = false;
-        if (partner) {
-            const double dx = (lane < b) ? ox - cpx : cpx - ox, dy = (lane < b) ? oy - cpy : cpy - oy;
+        {
+            const double dx = cpx - ox, dy = cpy - oy;
             const double d2 = fma(dy, dy, dx * dx);
-            surv = !(d2 > thr_b && d2 > ot);
+            surv = partner && !(d2 > thr_b && d2 > ot);
         }
-        if (__ballot_sync(FULL, surv) != mask0) break;
         // ---- narrow phase: one (partner, axis) item per lane ----------------------------------------------------
-        double nx = 0.0, ny = 0.0, cur = INFINITY;
-        bool sep = false;
-        if (active) {
-            double lo2, hi2;
-            if (freeaxis) {
-                const double ax = ey1 - ey0, ay = ex0 - ex1;
-                if (!(__double_as_longlong(ax) == __double_as_longlong(mmax) &&
-                      __double_as_longlong(ay) == __double_as_longlong(mmay))) {
-                    const double nrm = sqrt(fma(ay, ay, ax * ax));
-                    mnx = ax / nrm; mny = ay / nrm; mmax = ax; mmay = ay;
-                }
-                nx = mnx; ny = mny;
-                if (!(__double_as_longlong(nx) == __double_as_longlong(kx) &&
-                      __double_as_longlong(ny) == __double_as_longlong(ky))) {
-                    const double *g = s.sfix + v2 * 6;
-                    flo2 = fhi2 = dot2(nx, ny, g[0], g[1]);
-                    for (int v = 1; v < n2; v++) {
-                        const double c = dot2(nx, ny, g[v * 6], g[v * 6 + 1]);
-                        if (c < flo2) flo2 = c;
-                        if (c > fhi2) fhi2 = c;
-                    }
-                    kx = nx; ky = ny;
-                }
-                lo2 = flo2; hi2 = fhi2;
-            } else {
-                nx = cnx; ny = cny; lo2 = clo2; hi2 = chi2;
-            }
-            double lo1, hi1;
-            lo1 = hi1 = dot2(nx, ny, vtx[0], vty[0]);
-#pragma unroll
-            for (int v = 1; v < NM; v++) {
-                if (v < n1) {
-                    const double c = dot2(nx, ny, vtx[v], vty[v]);
-                    if (c < lo1) lo1 = c;
-                    if (c > hi1) hi1 = c;
+        {
+            // edge vector of b's edge (zero for a partner-axis lane: its key stays (0,0))
+            const double ax = ey1 - ey0, ay = ex0 - ex1;
+            const bool miss = (__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
+                              (__double_as_longlong(ay) != __double_as_longlong(keyy));
+            if (miss) {  // rare (<2%): new edge vector -> new unit normal (:790) and new partner bounds (:806-811)
+                const double nrm = sqrt(fma(ay, ay, ax * ax));
+                anx = ax / nrm; any_ = ay / nrm; keyx = ax; keyy = ay;
+                const double *g = s.sfix + v2 * 6;
+                alo2 = ahi2 = dot2(anx, any_, g[0], g[1]);
+                for (int v = 1; v < n2; v++) {
+                    const double c = dot2(anx, any_, g[v * 6], g[v * 6 + 1]);
+                    if (c < alo2) alo2 = c;
+                    if (c > ahi2) ahi2 = c;
                 }
             }
-            if (lo1 > lo2) {
-                double t = lo1; lo1 = lo2; lo2 = t;
-                t = hi1; hi1 = hi2; hi2 = t;
-            }
-            sep = hi1 < lo2;
-            cur = hi1 - lo2;
         }
+        double lo1, hi1;
+        lo1 = hi1 = dot2(anx, any_, vtx[0], vty[0]);                             // :795
+#pragma unroll
+        for (int v = 1; v < NM; v++) {                                           // :799-804
+            if (N1 || v < n1) {
+                const double c = dot2(anx, any_, vtx[v], vty[v]);
+                if (c < lo1) lo1 = c;
+                if (c > hi1) hi1 = c;
+            }
+        }
+        double lo2 = alo2, hi2 = ahi2;
+        if (lo1 > lo2) {                                                         // :815-817
+            double t = lo1; lo1 = lo2; lo2 = t;
+            t = hi1; hi1 = hi2; hi2 = t;
+        }
+        const bool sep = active && (hi1 < lo2);                                  // :820
+        const double cur = hi1 - lo2;                                            // :824
+        const unsigned survb = __ballot_sync(FULL, surv);
         const unsigned sepbits = __ballot_sync(FULL, sep);
-        const bool pair_sep = (sepbits & slot_mask) != 0;
-        const bool valid = active && (cur < INFINITY);
-        double bov = valid ? cur : INFINITY;
-        int bk = valid ? k : 99;
+        if (survb != mask0) break;
+        // slots whose pair has no separating axis
+        unsigned live = 0;
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            const double oov = __shfl_xor_sync(FULL, bov, o);
-            const int ok = __shfl_xor_sync(FULL, bk, o);
-            if (oov < bov || (oov == bov && ok < bk)) { bov = oov; bk = ok; }
-        }
-        const bool hit = (jj >= 0) && (k == 0) && !pair_sep && (bk != 99);
-        const unsigned hitb = __ballot_sync(FULL, hit);
-        if (__popc(hitb) != 1) break;  // zero tuples: the resolve loop ends; several: general path
-        const int hl = __ffs(hitb) - 1;                       // leader lane of the colliding partner's slot
-        const int wk = __shfl_sync(FULL, bk, hl);
-        const double mag = __shfl_sync(FULL, bov, hl);
-        const double ux = __shfl_sync(FULL, nx, hl + wk) * -1.0, uy = __shfl_sync(FULL, ny, hl + wk) * -1.0;
+        for (int q = 0; q < 4; q++)
+            if (!((sepbits >> (8 * q)) & 0xffu)) live |= 1u << q;
+        live &= live_all;
+        if (__popc(live) != 1) break;  // zero tuples: the resolve loop ends; several: general path
+        const int sl = __ffs(live) - 1;
+        // first strict minimum in axis order (:827-830) over the 8 lanes of slot sl.  Overlaps of a non-separated
+        // pair are >= +0.0, so their bit patterns order like unsigned integers: two 32-bit redux.sync.min.
+        const bool mine = active && (slot == sl) && (cur < INFINITY);
+        // (-0.0 orders like +0.0: `cur < overlap` is false between them and the push n*(mag+EPSILON) is the same)
+        const unsigned long long bits = (cur == 0.0) ? 0ull : (unsigned long long)__double_as_longlong(cur);
+        const unsigned khi = mine ? (unsigned)(bits >> 32) : 0xffffffffu;
+        const unsigned mhi = __reduce_min_sync(FULL, khi);
+        if (mhi == 0xffffffffu) break;  // no comparable overlap (NaN axes): general path
+        const unsigned klo = (mine && khi == mhi) ? (unsigned)bits : 0xffffffffu;
+        const unsigned mlo = __reduce_min_sync(FULL, klo);
+        const unsigned winb = __ballot_sync(FULL, mine && khi == mhi && (unsigned)bits == mlo);
+        if (winb == 0) break;
+        const int wl = __ffs(winb) - 1;  // lowest axis index among equal minima
+        const double mag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        const double ux = __shfl_sync(FULL, anx, wl) * -1.0, uy = __shfl_sync(FULL, any_, wl) * -1.0;  // :838-839
         ncalls++;
         ncalls_total++;
         // ---- resolution, free body vs fixed body (:171-198) -----------------------------------------------------
-        const double sc = mag + kp.eps;
+        const double sc = mag + kp.eps;                                          // :158
         const double nvx = ux * sc, nvy = uy * sc;
 #pragma unroll
-        for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }
+        for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }           // :174
         ex0 += nvx; ey0 += nvy; ex1 += nvx; ey1 += nvy;
-        if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }
-        const double vdotN = dot2(cvx, cvy, ux, uy);
-        const double cc = kp.ope * vdotN;
+        if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }   // :180-181
+        const double vdotN = dot2(cvx, cvy, ux, uy);                             // :183
+        const double cc = kp.ope * vdotN;                                        // :188
         cvx -= cc * ux;
         cvy -= cc * uy;
-        heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);
+        heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
     }
     // ---- write the state back for the general path ----------------------------------------------------------------
     __syncwarp();
 #pragma unroll
     for (int v = 0; v < NM; v++)
         if (lane == v && v < n1) { s.vert[2 * (v1 + v)] = vtx[v]; s.vert[2 * (v1 + v) + 1] = vty[v]; }
-    if (freeaxis && slot == 0) { s.max_[v1 + k] = mmax; s.may_[v1 + k] = mmay; s.mnx[v1 + k] = mnx; s.mny[v1 + k] = mny; }
+    if (freeaxis && slot == 0 && keyx == keyx) {
+        s.max_[v1 + k] = keyx; s.may_[v1 + k] = keyy; s.mnx[v1 + k] = anx; s.mny[v1 + k] = any_;
+    }
     if (lane == 0) {
         s.px[b] = cpx; s.py[b] = cpy; s.vx[b] = cvx; s.vy[b] = cvy; s.sx[b] = cpx; s.sy[b] = cpy;
     }
     __syncwarp();
 }
-
 
 __global__ void __launch_bounds__(CONTACT_BLOCK, 3)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
@@ -698,8 +696,10 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 resolve = true;  // next round: check_collisions() at :234
                 if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F) {
                     const int b = s.hi[0];
-                    if (kp.nv[b] <= 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
-                    else if (kp.nv[b] <= 8) fast_resolve<8>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                    const int nb = kp.nv[b];
+                    if (nb == 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                    else if (nb == 3) fast_resolve<3>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                    else if (nb <= 8) fast_resolve<0>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
                 }
                 continue;
             }
