@@ -85,8 +85,10 @@ def build_spec(args, rank, world_size):
     import fizz2d_b200 as fz
     from fizz2d_b200.batch import GroupSpec
     sc = fz.load_in(os.path.join(ROOT, "simulations", SCENE + ".in"))
+    from fizz2d_b200 import distributed as fd
     total = args.worlds * world_size
-    deltas = fz.perturbation_deltas(SEED, total, sc.n_free)[rank * args.worlds:(rank + 1) * args.worlds]
+    idx = fd.shard_indices(total, rank, world_size)          # interleaved: world w lives on rank w % G
+    deltas = fz.perturbation_deltas(SEED, total, sc.n_free)[idx]
     return GroupSpec.from_scene(sc, args.worlds, np.ascontiguousarray(deltas), max_calls=args.max_calls)
 
 
@@ -191,19 +193,18 @@ def run_gpu(args):
     peak_tflops, _ = fz.fp64_peak(local_rank, 4096)
     h2d_bytes = 8 * W * (spec.pos.shape[0] + spec.vel.shape[0] + spec.off.shape[0] + spec.thr.shape[0] + spec.mass.shape[0])
     d2h_bytes = 8 * W * (4 + 1 + 1)
-    gathered = torch.empty((world_size, 6, W), dtype=torch.float64, device=dev) if world_size > 1 else None
+    from fizz2d_b200 import distributed as fd
 
     def stepping():
         bw.step(args.timesteps)
 
     def gather_results():
+        # the one collective of the path: end-of-run gather of [E,K,P,H,fitness,status] per world (NCCL)
         if world_size > 1:
-            local = torch.empty((6, W), dtype=torch.float64, device=dev)
             fz.lib.check(fz.lib.load().fizz_energy(g.handle, torch.cuda.current_stream().cuda_stream))
-            local[:4] = g.section("energy", 4)
-            local[4] = g.section("heat", 1)[0]                      # fitness := dissipated energy
-            local[5] = g.section("status", 1, torch.int64)[0].double()
-            dist.all_gather_into_tensor(gathered.view(-1), local.view(-1))
+            local = fd.pack_results(g.section("energy", 4), g.section("heat", 1)[0],      # fitness := heat
+                                    g.section("status", 1, torch.int64)[0])
+            return fd.gather_results(local, W * world_size)
 
     def pass_resident():
         bw.restore(state0)
@@ -231,6 +232,7 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = bw.kernel_info()[0]["launches"]
+    bw.counters(reset=True)
     bw.profile(reset=True)
     bw.set_profiling(True)
     pass_ms = []
@@ -246,6 +248,7 @@ def run_gpu(args):
     sampler.stop_flag = True
     launches = bw.kernel_info()[0]["launches"] - launches0
     prof = bw.profile(reset=True)[0]
+    cnt = bw.counters(reset=True)[0]
     bw.set_profiling(False)
     t_ms = sum(a.elapsed_time(b) for a, b in pass_ms)
     steps_done = bw.steps_done()
@@ -312,17 +315,37 @@ def run_gpu(args):
                                     "python_reference_note": "the Python reference itself ran at 384 world-steps/s/core "
                                                              "on this scene in the build container (BASELINE.md)"}
             line["worlds"]["sample_capped_fraction"] = r["capped"] / r["n"]
-        # ---- roofline of the dominant kernel (FP64 pipe binds; HBM traffic is 2*S bytes per world per launch) ------
-        kern_s = sum(prof[k][0] for k in prof) * 1e-3
-        if ops_per_ws is not None:
-            achieved = ops_per_ws * world_steps * args.steps / kern_s / 1e12
-            line["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                                "frac": achieved / peak_tflops, "traffic": None,
-                                "ops_per_world_step": ops_per_ws,
-                                "peak_source": "fizz_fp64_peak(): DFMA microbenchmark run on this GPU at bench start "
-                                               "(MEASURED_PEAKS.json has no FP64 figure)",
-                                "hbm": {"algorithmic_bytes_per_launch": 8 * W * (2 * L.state_words // L.stride),
-                                        "note": "state is read once and written once per launch; HBM is not the bound"}}
+        # ---- rooflines: the FP64 pipe binds (state stays on chip: HBM sees 2*S bytes per world per launch) -------
+        # ALGORITHMIC ops follow SURVEY 8d: a quiescent world-step is 12F + 2V + 8P ops (closed form), the mean over
+        # all world-steps is measured by the op-counting CPU restatement on the sample above.
+        F_, X_, V_ = spec.n_free, spec.n_fixed, sum(spec.nverts_free)
+        P_ = F_ * (F_ - 1) // 2 + F_ * X_
+        q_ops = 12 * F_ + 2 * V_ + 8 * P_
+        line["work"] = {k: int(v) // args.steps for k, v in cnt.items()}
+        if ops_per_ws is not None and args.mode == "hybrid":
+            total_ops = ops_per_ws * world_steps * args.steps
+            b_ops = q_ops * cnt["ballistic_world_steps"]
+            rk = {}
+            for name, ops in (("ballistic", b_ops), ("contact", max(0.0, total_ops - b_ops))):
+                sec = prof[name][0] * 1e-3
+                if sec > 0:
+                    rk[name] = {"bound": "fp64", "achieved": ops / sec / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+                                "frac": ops / sec / 1e12 / peak_tflops, "ms_per_pass": prof[name][0] / args.steps}
+            line["roofline_by_kernel"] = rk
+            line["roofline"] = dict(rk[dom], traffic=None, kernel=dom + "_kernel", ops_per_world_step=ops_per_ws,
+                                    quiescent_ops_per_world_step=q_ops,
+                                    peak_source="fizz_fp64_peak(): DFMA microbenchmark on this GPU at bench start "
+                                                "(MEASURED_PEAKS.json has no FP64 figure)",
+                                    note="the dominant kernel is latency-bound: a pass ends when the world with the "
+                                         "longest sequential chain of resolve passes ends (DESIGN.md, 'critical path')",
+                                    hbm={"algorithmic_bytes_per_chunk": 8 * W * 2 * (4 * F_ + 1),
+                                         "note": "pos+vel+heat read and written once per chunk; HBM is not the bound"})
+        elif ops_per_ws is not None:
+            sec = sum(prof[k][0] for k in prof) * 1e-3
+            ach = ops_per_ws * world_steps * args.steps / sec / 1e12
+            line["roofline"] = {"bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+                                "frac": ach / peak_tflops, "traffic": None, "kernel": "step_kernel",
+                                "ops_per_world_step": ops_per_ws}
         print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()

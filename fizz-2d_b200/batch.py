@@ -376,6 +376,16 @@ class BatchedWorld:
             out.append({"thread": (ms[0], n[0]), "ballistic": (ms[1], n[1]), "contact": (ms[2], n[2])})
         return out
 
+    def counters(self, reset=True):
+        """Per group: device-side work counters since the last reset (hybrid mode)."""
+        out = []
+        for k, g in enumerate(self.groups):
+            a = (C.c_int64 * 4)()
+            _lib.check(_lib.load().fizz_counters(g.handle, a, 1 if reset else 0, C.c_void_p(self._stream_ptr(k))))
+            out.append(dict(ballistic_world_steps=a[0], contact_world_steps=a[1], contact_calls=a[2],
+                            fast_path_calls=a[3]))
+        return out
+
     def kernel_info(self):
         info = []
         for g in self.groups:

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(BALLISTIC_BLOCK) ballistic_kernel(const __grid
         kp.steps[w] = step;
         kp.calls[w] += step - step0;  // one state-relevant check_collisions() per quiescent step
         kp.vflag[w] = 0;              // vertices are derived: off + com
+        atomicAdd(kp.counters + 0, (unsigned long long)(step - step0));  // compiler warp-aggregates (REDUX)
     }
 }
 

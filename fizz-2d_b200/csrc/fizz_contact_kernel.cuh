@@ -452,8 +452,9 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
         for (int v = lane; v < V; v += 32) s.max_[v] = NAN;  // empty memo: NaN never compares equal
         double heat = kp.heat[w];
         long long step = kp.steps[w];
+        const long long step_in = step;
         long long status = 0;
-        long long ncalls_total = 0;
+        long long ncalls_total = 0, fast_calls = 0;
         __syncwarp();
 
         bool resolve = false, verts_explicit = false;
@@ -696,10 +697,12 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 resolve = true;  // next round: check_collisions() at :234
                 if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F) {
                     const int b = s.hi[0];
+                    const long long before = ncalls_total;
                     const int nb = kp.nv[b];
                     if (nb == 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
                     else if (nb == 3) fast_resolve<3>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
                     else if (nb <= 8) fast_resolve<0>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                    fast_calls += ncalls_total - before;
                 }
                 continue;
             }
@@ -746,6 +749,9 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             kp.steps[w] = step;
             kp.calls[w] += ncalls_total;
             kp.vflag[w] = verts_explicit ? 1 : 0;
+            atomicAdd(kp.counters + 1, (unsigned long long)(step - step_in));
+            atomicAdd(kp.counters + 2, (unsigned long long)ncalls_total);
+            atomicAdd(kp.counters + 3, (unsigned long long)fast_calls);
         }
         __syncwarp();
     }

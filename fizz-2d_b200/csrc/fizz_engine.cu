@@ -256,6 +256,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     kp.off = s + L.off; kp.thr = s + L.thr; kp.mass = s + L.mass; kp.verts = s + L.verts;
     g->sched_list = (long long *)(s + L.sched);
     g->sched_count = (unsigned long long *)(s + L.sched + L.stride);
+    kp.counters = g->sched_count + 4;
     kp.W = L.n_worlds; kp.Wp = L.stride;
     kp.F = L.n_free; kp.X = L.n_fixed; kp.V = L.n_free_verts;
     const int F = kp.F, X = kp.X;
@@ -517,6 +518,16 @@ int fizz_download(FizzGroup *g, double *pos, double *vel, double *heat, double *
     if (status && (rc = copy_rows((double *)status, s + L.status, 1, W, Wp, cudaMemcpyDeviceToHost, st))) return rc;
     if (steps && (rc = copy_rows((double *)steps, s + L.steps, 1, W, Wp, cudaMemcpyDeviceToHost, st))) return rc;
     if (calls && (rc = copy_rows((double *)calls, s + L.calls, 1, W, Wp, cudaMemcpyDeviceToHost, st))) return rc;
+    return FIZZ_OK;
+}
+
+int fizz_counters(FizzGroup *g, int64_t *out4, int32_t reset, void *stream) {
+    if (!g || !out4) return fail(FIZZ_E_ARG, "fizz_counters: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(g->device));
+    CU(cudaMemcpyAsync(out4, g->kp.counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (reset) CU(cudaMemsetAsync(g->kp.counters, 0, 4 * sizeof(int64_t), st));
     return FIZZ_OK;
 }
 

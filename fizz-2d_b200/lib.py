@@ -64,6 +64,7 @@ EXPORTS = {
     "fizz_snapshot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fizz_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "fizz_vertices": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fizz_counters": (C.c_int, [C.c_void_p, lp, C.c_int32, C.c_void_p]),
     "fizz_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "fizz_profile_read": (C.c_int, [C.c_void_p, dp, lp, C.c_int32]),
     "fizz_fp64_peak": (C.c_int, [C.c_int, C.c_int32, dp, dp]),

@@ -187,6 +187,11 @@ int fizz_kernel_info(FizzGroup *g, int32_t which, int32_t *regs_per_thread, int3
 int fizz_set_profiling(FizzGroup *g, int32_t enabled);
 int fizz_profile_read(FizzGroup *g, double *ms3, int64_t *launches3, int32_t reset);
 
+/* Work counters accumulated on the device since the last reset (synchronises `stream`):
+ * out4[0] world-steps advanced by the ballistic kernel, [1] by the contact kernel, [2] check_collisions() calls made
+ * by the contact kernel, [3] of those inside its single-contact fast path.  Thread mode does not count. */
+int fizz_counters(FizzGroup *g, int64_t *out4, int32_t reset, void *stream);
+
 /* FP64 FMA throughput microbenchmark (the roofline denominator MEASURED_PEAKS.json lacks): runs `iters`
  * dependent-chain DFMA rounds on every SM of `device` and returns achieved TFLOP/s (FMA = 2 flops). */
 int fizz_fp64_peak(int device, int32_t iters, double *tflops, double *ms);
