@@ -281,7 +281,7 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     if (jj >= 0) { n2 = kp.nv[jj]; v2 = kp.vs[jj]; }
     const bool active = (jj >= 0) && (k < n1 + n2);
     const bool freeaxis = active && (k < n1);
-    const unsigned live_all = (ncand >= 4) ? 0xfu : ((1u << ncand) - 1u);
+    const unsigned live_bytes_all = (ncand >= 4) ? 0xffffffffu : ((1u << (8 * ncand)) - 1u);
     // axis registers of this lane: unit normal, the partner's projection bounds on it, and -- for an edge of b -- the
     // edge end points plus the exact edge vector the normal was computed from (memo key; NaN = not computed yet).
     double anx = 0.0, any_ = 0.0, alo2 = 0.0, ahi2 = 0.0;
@@ -341,27 +341,22 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         const double cur = hi1 - lo2;                                            // :824
         const unsigned survb = __ballot_sync(FULL, surv);
         const unsigned sepbits = __ballot_sync(FULL, sep);
-        if (survb != mask0) break;
-        // slots whose pair has no separating axis
-        unsigned live = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (!((sepbits >> (8 * q)) & 0xffu)) live |= 1u << q;
-        live &= live_all;
-        if (__popc(live) != 1) break;  // zero tuples: the resolve loop ends; several: general path
-        const int sl = __ffs(live) - 1;
-        // first strict minimum in axis order (:827-830) over the 8 lanes of slot sl.  Overlaps of a non-separated
+        // slots (bytes of sepbits) whose pair has no separating axis; exactly one of the candidate slots may be live
+        const unsigned livebytes = __vcmpeq4(sepbits, 0u) & live_bytes_all;   // 0xff per live slot
+        const bool my_live = (livebytes >> (8 * slot)) & 1u;
+        // first strict minimum in axis order (:827-830) over the 8 lanes of the live slot.  Overlaps of a non-separated
         // pair are >= +0.0, so their bit patterns order like unsigned integers: two 32-bit redux.sync.min.
-        const bool mine = active && (slot == sl) && (cur < INFINITY);
         // (-0.0 orders like +0.0: `cur < overlap` is false between them and the push n*(mag+EPSILON) is the same)
+        const bool mine = active && my_live && (cur < INFINITY);
         const unsigned long long bits = (cur == 0.0) ? 0ull : (unsigned long long)__double_as_longlong(cur);
         const unsigned khi = mine ? (unsigned)(bits >> 32) : 0xffffffffu;
         const unsigned mhi = __reduce_min_sync(FULL, khi);
-        if (mhi == 0xffffffffu) break;  // no comparable overlap (NaN axes): general path
         const unsigned klo = (mine && khi == mhi) ? (unsigned)bits : 0xffffffffu;
         const unsigned mlo = __reduce_min_sync(FULL, klo);
         const unsigned winb = __ballot_sync(FULL, mine && khi == mhi && (unsigned)bits == mlo);
-        if (winb == 0) break;
+        // one exit test per pass: other candidate set | zero or several colliding partners (the resolve loop ends,
+        // or the general path takes over) | no comparable overlap (NaN axes)
+        if (survb != mask0 || __popc(livebytes) != 8 || mhi == 0xffffffffu || winb == 0) break;
         const int wl = __ffs(winb) - 1;  // lowest axis index among equal minima
         const double mag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
         const double ux = __shfl_sync(FULL, anx, wl) * -1.0, uy = __shfl_sync(FULL, any_, wl) * -1.0;  // :838-839
