@@ -38,27 +38,44 @@ __global__ void __launch_bounds__(BALLISTIC_BLOCK) ballistic_kernel(const __grid
     }
     const double dt = kp.time_disc;
     long long step = step0;
+    // CONSERVATIVE threshold test on the integer pipe.  s = fma(dy,dy,dx*dx) is >= +0.0 (or NaN), and for
+    // non-negative doubles the bit patterns order like integers, so  hi32(s) > hi32(T)  implies  s > T.  A pair is
+    // counted as "skipped by the broad phase" only when that holds for both thresholds; anything else -- a pair
+    // that passes, or one within 2^-20 of its threshold -- ends the ballistic run and the contact kernel repeats the
+    // step with the exact test.  The FP64 pipe is left with the 4 arithmetic ops per pair.  A NaN/inf coordinate
+    // (whose pairs the reference does NOT skip: `nan > r` is False, physics.py:278) is caught by the exponent test.
+    int thr_h[F];
+#pragma unroll
+    for (int b = 0; b < F; b++) thr_h[b] = __double2hiint(thr[b]);
     while (step < kp.target_steps) {
-        // dist > max(r_i, r_j)  <=>  s > T(r_i) && s > T(r_j), s = fma(dy,dy,dx*dx)  (:277-278; T: see fizz_b200.h)
         bool any = false;
 #pragma unroll
         for (int i = 0; i < F; i++) {
 #pragma unroll
             for (int j = i + 1; j < F; j++) {
                 const double dx = px[i] - px[j], dy = py[i] - py[j];
-                const double s = fma(dy, dy, dx * dx);
-                any |= !(s > thr[i] && s > thr[j]);
+                const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                any |= !(sh > max(thr_h[i], thr_h[j]));
             }
         }
         for (int j = 0; j < X; j++) {
-            const double cx = kp.fcx[j], cy = kp.fcy[j], ft = kp.fthr[j];
+            const double cx = kp.fcx[j], cy = kp.fcy[j];
+            const int fh = __double2hiint(kp.fthr[j]);
 #pragma unroll
             for (int i = 0; i < F; i++) {
                 const double dx = px[i] - cx, dy = py[i] - cy;
-                const double s = fma(dy, dy, dx * dx);
-                any |= !(s > thr[i] && s > ft);
+                const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                any |= !(sh > max(thr_h[i], fh));
             }
         }
+        // non-finite coordinates: exponent field all ones (integer pipe); such a world goes to the contact kernel
+        unsigned expo = 0;
+#pragma unroll
+        for (int b = 0; b < F; b++) {
+            const unsigned hx = (unsigned)__double2hiint(px[b]) & 0x7ff00000u, hy = (unsigned)__double2hiint(py[b]) & 0x7ff00000u;
+            expo |= (hx == 0x7ff00000u) | (hy == 0x7ff00000u);
+        }
+        any |= expo != 0;
         if (any) break;  // a pair reaches the narrow phase: hand the world to the contact kernel at this step
 #pragma unroll
         for (int b = 0; b < F; b++) {
