@@ -163,11 +163,7 @@ class BatchedWorld:
                 o += s.n_worlds
         self.groups: List[_Group] = [_Group(s, device, np.asarray(ids)) for s, ids in zip(specs, world_ids)]
         self.n_worlds = sum(s.n_worlds for s in specs)
-        self._where = {}
-        for gi, g in enumerate(self.groups):
-            for k, wid in enumerate(g.world_ids):
-                if self.n_worlds <= 1 << 16:
-                    self._where[int(wid)] = (gi, k)
+        self._where = None
         self.streams = [torch.cuda.Stream(device=device) for _ in self.groups] if len(self.groups) > 1 else [None]
         self.steps_requested = 0
         self.upload()
@@ -184,6 +180,41 @@ class BatchedWorld:
     def from_text(cls, text, n_worlds=1, deltas=None, gravity=(0.0, 0.0), max_calls=4096, device=0):
         sc = _scene.parse_in(text)
         return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls)], device=device)
+
+    @classmethod
+    def from_mixed(cls, paths, n_worlds, seed=0, perturb=True, dpos=5.0, dvel=30.0, max_calls=4096, device=0):
+        """Mixed batch: world w runs scene paths[w % len(paths)].  One perturbation row of
+        max(F) bodies is drawn per world; a scene with fewer bodies uses the first rows.  One group (one resident
+        scene descriptor, own stream) per scene; world order is preserved by `world_ids`."""
+        scenes = [_scene.load_in(p) for p in paths]
+        fmax = max(sc.n_free for sc in scenes)
+        deltas = _scene.perturbation_deltas(seed, n_worlds, fmax, dpos, dvel) if perturb else np.zeros((n_worlds, fmax, 4))
+        specs, ids = [], []
+        for k, sc in enumerate(scenes):
+            idx = np.arange(k, n_worlds, len(scenes))
+            if len(idx) == 0:
+                continue
+            d = np.ascontiguousarray(deltas[idx][:, :sc.n_free, :])
+            specs.append(GroupSpec.from_scene(sc, len(idx), d, max_calls=max_calls))
+            ids.append(idx)
+        return cls(specs, ids, device=device)
+
+    @classmethod
+    def from_ga(cls, scene_path, n_worlds, seed=0, max_calls=4096, device=0, population=None):
+        """GA population: the scene's fixed geometry, its free bodies replaced by ONE random
+        convex polygon per world (fizz2d_b200.ga).  Worlds are grouped by vertex count (one kernel topology each)."""
+        from . import ga as _ga
+        sc = _scene.load_in(scene_path)
+        nverts, pts, vel = population if population is not None else _ga.random_convex_polygons(seed, n_worlds)
+        base = _scene.Scene(sc.width, sc.height, dict(sc.params), [], sc.fixed, sc.name)
+        specs, ids = [], []
+        for n in sorted(set(int(x) for x in nverts)):
+            idx = np.nonzero(nverts == n)[0]
+            P = np.stack([pts[w] for w in idx])
+            specs.append(GroupSpec(base, [np.ascontiguousarray(P)], vel[idx][:, None, :].copy(),
+                                   np.ones((len(idx), 1)), max_calls=max_calls))
+            ids.append(idx)
+        return cls(specs, ids, device=device)
 
     def close(self):
         for g in self.groups:
@@ -319,12 +350,21 @@ class BatchedWorld:
 
     def dump_world(self, i, verts=None):
         """str(world) of world i (physics.py:291-301, :713-722, :600-606): int() truncation, clamp to the frame."""
-        gi, k = self._where[int(i)]
+        gi, k = self.locate(i)
         g = self.groups[gi]
         if verts is None:
             verts = self.vertices()
             verts = verts if len(self.groups) == 1 else verts[gi]
         return format_world(g.spec, verts[k])
+
+    def locate(self, i):
+        """(group index, index inside the group) of global world i."""
+        if self._where is None:
+            self._where = {}
+            for gi, g in enumerate(self.groups):
+                for k, wid in enumerate(g.world_ids):
+                    self._where[int(wid)] = (gi, k)
+        return self._where[int(i)]
 
     # -- contact trace (tests) ---------------------------------------------------------------------------
     def enable_trace(self, capacity=1 << 20):

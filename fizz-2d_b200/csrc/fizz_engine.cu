@@ -82,9 +82,21 @@ struct KernelInfo {
     int blocks_per_sm;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process-wide: it must only ever grow, or a group
+// with a smaller footprint created later would make the launches of an earlier, larger group invalid.
+template <typename K>
+cudaError_t raise_dynamic_smem(K kernel, size_t smem, size_t *current) {
+    const size_t want = smem > 48 * 1024 ? smem : 48 * 1024;
+    if (want <= *current) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e == cudaSuccess) *current = want;
+    return e;
+}
+
 template <int F>
 cudaError_t prep_thread(size_t smem, KernelInfo *ki) {
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t current = 0;
+    cudaError_t e = raise_dynamic_smem(step_kernel<F>, smem, &current);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&ki->attr, step_kernel<F>);
     if (e != cudaSuccess) return e;
@@ -316,7 +328,10 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     FIZZ_DISPATCH_F(F, e = prep_ballistic<FF>(&g->ballistic_ki));
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "ballistic kernel setup"); }
     g->contact_smem = contact_smem_bytes(kp.V, kp.FV);
-    e = cudaFuncSetAttribute(contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->contact_smem);
+    {
+        static size_t current = 0;
+        e = raise_dynamic_smem(contact_kernel, g->contact_smem, &current);
+    }
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&g->contact_ki.attr, contact_kernel);
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->contact_ki.blocks_per_sm, contact_kernel, CONTACT_BLOCK,

@@ -128,6 +128,44 @@ def gen_perturbed(tag, scene_for_world, deltas, worlds, nsteps, checkpoints, max
           time.time() - t0, os.path.getsize(fn) // 1024))
 
 
+def gen_ga(tag, scene, seed, worlds, nsteps, checkpoints, max_calls):
+    """GA population: the reference run on scene text = fixed geometry + one random polygon."""
+    t0 = time.time()
+    sc = fz.load_in(scene_path(scene))
+    nverts, pts, vel = fz.ga.random_convex_polygons(seed, max(worlds) + 1)
+    rec = dict(worlds=np.array(worlds, dtype=np.int64), checkpoints=np.array(checkpoints, dtype=np.int64),
+               max_calls=np.int64(max_calls), nsteps=np.int64(nsteps), scene=np.array(scene), seed=np.int64(seed),
+               scene_text=np.array(open(scene_path(scene)).read()))
+    for wi in worlds:
+        text = fz.ga.fixed_scene_text(sc) + fz.ga.polygon_in_text(pts[wi], vel[wi])
+        w = rh.RefWorld(text=text, max_calls=max_calls)
+        ic = init_arrays(w)
+        pre = "w%d_" % wi
+        rec[pre + "points"] = pts[wi]
+        rec[pre + "vel"] = vel[wi]
+        for t in range(nsteps):
+            if not w.update():
+                break
+            if (t + 1) in checkpoints:
+                rec[pre + "com_at_%d" % (t + 1)] = w.com()
+        ci, cf = contacts_arrays(w)
+        rec[pre + "final_com"] = w.com()
+        rec[pre + "final_verts"] = np.concatenate(w.verts())
+        rec[pre + "final_heat"] = np.float64(w.heat())
+        rec[pre + "final_energy"] = w.energy()
+        rec[pre + "steps_done"] = np.int64(w.step_index)
+        rec[pre + "capped_at"] = np.int64(w.capped_at)
+        rec[pre + "calls"] = np.array(w.calls_per_step, dtype=np.int32)
+        rec[pre + "contacts_idx"] = ci
+        rec[pre + "contacts_val"] = cf
+        for key in ("init_com", "init_vel", "init_radius", "init_mass", "init_offx", "init_offy"):
+            rec[pre + key] = ic[key]
+    fn = os.path.join(OUT, "ga_%s.npz" % tag)
+    np.savez_compressed(fn, **rec)
+    print("%-44s %3d worlds x %d steps  %.1fs  %d KB" % (os.path.basename(fn), len(worlds), nsteps, time.time() - t0,
+          os.path.getsize(fn) // 1024))
+
+
 def gen_anchors():
     """The SURVEY 8c table: 1000 steps, sha256 over str(world) after each step, over the energy rows written
     before each step, and over the contact list 'step:call#:i-j' of every check_collisions call (incl. the two
@@ -177,6 +215,7 @@ def main():
     d = fz.perturbation_deltas(20260004, 262144, 3)
     gen_perturbed("config4_mixed", lambda w: "2CHAMBERS_3BALLS" if w % 2 == 0 else "STACKEDCHAMBERS_1SQUARE", d,
                   list(range(1, 13)), 300, [100, 200, 300], 256)
+    gen_ga("config5_pentagonvoid", "PENTAGONVOID_1SQUARE", 20260005, list(range(0, 24)), 300, [100, 200, 300], 256)
     gen_anchors()
 
 

@@ -115,3 +115,36 @@ def test_oracle_perturbed_worlds(tag):
         want = contact_rows(g[pre + "contacts_idx"], g[pre + "contacts_val"])
         assert [c[:4] for c in got] == [c[:4] for c in want], wi
         assert np.array_equal(bits([c[4:] for c in got]), bits([c[4:] for c in want])), wi
+
+
+def test_oracle_ga_population():
+    """GA worlds: the oracle (own parser + init math on the same text the reference got)
+    equals the reference, and the committed population is what the generator produces."""
+    import fizz2d_b200 as fz
+    g = golden("ga_config5_pentagonvoid")
+    sc = fz.parse_in(str(g["scene_text"]))
+    nverts, pts, vel = fz.ga.random_convex_polygons(int(g["seed"]), int(g["worlds"].max()) + 1)
+    for wi in g["worlds"]:
+        pre = "w%d_" % wi
+        assert np.array_equal(bits(pts[wi]), bits(g[pre + "points"])) and np.array_equal(bits(vel[wi]), bits(g[pre + "vel"]))
+        text = fz.ga.fixed_scene_text(sc) + fz.ga.polygon_in_text(g[pre + "points"], g[pre + "vel"])
+        ow = orc.OracleWorld.from_text(text, max_calls=int(g["max_calls"]), trace_cap=1 << 16)
+        assert np.array_equal(bits(ow.com()[0, :2]), bits(g[pre + "init_com"][0]))
+        calls = []
+        for t in range(int(g["nsteps"])):
+            ok = ow.update()
+            calls.append(ow.calls_last_step())
+            if not ok:
+                break
+            key = pre + "com_at_%d" % (t + 1)
+            if key in g.files:
+                assert np.array_equal(bits(ow.com()), bits(g[key])), (wi, t)
+        assert ow.steps_done() == int(g[pre + "steps_done"])
+        assert (ow.status() == 1) == (int(g[pre + "capped_at"]) >= 0)
+        assert np.array_equal(bits(ow.com()), bits(g[pre + "final_com"])), wi
+        assert np.array_equal(bits(ow.verts()), bits(g[pre + "final_verts"])), wi
+        assert bits(ow.heat()) == bits(g[pre + "final_heat"])
+        assert calls == list(g[pre + "calls"]), wi
+        got, want = ow.contacts(), contact_rows(g[pre + "contacts_idx"], g[pre + "contacts_val"])
+        assert [c[:4] for c in got] == [c[:4] for c in want], wi
+        assert np.array_equal(bits([c[4:] for c in got]), bits([c[4:] for c in want])), wi
