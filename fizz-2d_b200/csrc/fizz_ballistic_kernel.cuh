@@ -19,12 +19,14 @@ namespace fizz {
 constexpr int BALLISTIC_BLOCK = 128;
 
 template <int F>
-__global__ void __launch_bounds__(BALLISTIC_BLOCK) ballistic_kernel(const __grid_constant__ KParams kp) {
-    const long long w = (long long)blockIdx.x * BALLISTIC_BLOCK + threadIdx.x;
-    if (w >= kp.W) return;
-    if (kp.status[w] != 0) return;
+__global__ void __launch_bounds__(BALLISTIC_BLOCK)
+ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
+                 const unsigned long long *__restrict__ count_ptr) {
+    // threads map to the compacted live list (ascending world index inside a warp: rows stay mostly coalesced)
+    const long long t = (long long)blockIdx.x * BALLISTIC_BLOCK + threadIdx.x;
+    if (t >= (long long)*count_ptr) return;
+    const long long w = list[t];
     const long long step0 = kp.steps[w];
-    if (step0 == 0 || step0 >= kp.target_steps) return;
     const long long Wp = kp.Wp;
     const int X = kp.X;
     double px[F], py[F], vx[F], vy[F], thr[F];
@@ -98,7 +100,23 @@ __global__ void __launch_bounds__(BALLISTIC_BLOCK) ballistic_kernel(const __grid
         kp.calls[w] += step - step0;  // one state-relevant check_collisions() per quiescent step
         kp.vflag[w] = 0;              // vertices are derived: off + com
         atomicAdd(kp.counters + 0, (unsigned long long)(step - step0));  // compiler warp-aggregates (REDUX)
+    } else {
+        kp.tier[w] = 1;  // no progress: the world is in a contact phase; the contact kernel clears the hint
     }
+}
+
+// Live list of the ballistic kernel: running worlds past step 0, short of the target, not hinted "contact phase".
+__global__ void live_kernel(const long long *status, const long long *steps, const long long *tier, long long W,
+                            long long target, long long *list, unsigned long long *count) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = (w < W) && status[w] == 0 && tier[w] == 0 && steps[w] > 0 && steps[w] < target;
+    const unsigned b = __ballot_sync(0xffffffffu, live);
+    if (b == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) list[base + __popc(b & ((1u << lane) - 1u))] = w;
 }
 
 }  // namespace fizz

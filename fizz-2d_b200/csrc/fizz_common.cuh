@@ -21,7 +21,7 @@ constexpr int MAX_PAIRS = FIZZ_MAX_FREE * (FIZZ_MAX_FREE - 1) / 2 + FIZZ_MAX_FRE
 struct KParams {
     // slab sections (row r of a section starts at ptr + r*Wp; element w of a row is world w)
     double *pos, *vel, *heat;
-    long long *status, *steps, *calls, *vflag;
+    long long *status, *steps, *calls, *vflag, *tier;
     const double *off, *thr, *mass;
     double *verts;
     const double *fixed_geom;  // [FV][6]: x, y, unit normal of edge k->k+1 (nx, ny), own projection (lo, hi)

@@ -454,6 +454,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 
         bool resolve = false, verts_explicit = false;
         int k = 0, ncalls = 0, ns = 0;
+        int quiet = 0;  // consecutive timesteps with an empty broad phase (scheduling hint only)
         double dt = kp.time_disc;
 
         while (true) {
@@ -718,6 +719,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             if (lane < F) { s.sx[lane] = s.px[lane]; s.sy[lane] = s.py[lane]; }  // finish_update (:237-239, :251)
             __syncwarp();
             step++;                                            // :259
+            quiet = (ncalls == 1 && ns == 0) ? quiet + 1 : 0;
             resolve = false; k = 0; dt = kp.time_disc; ncalls = 0;
             if (step >= kp.target_steps) break;
             verts_explicit = false;
@@ -744,6 +746,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             kp.steps[w] = step;
             kp.calls[w] += ncalls_total;
             kp.vflag[w] = verts_explicit ? 1 : 0;
+            kp.tier[w] = (quiet >= 8) ? 0 : 1;  // back to the ballistic kernel after 8 quiescent steps
             atomicAdd(kp.counters + 1, (unsigned long long)(step - step_in));
             atomicAdd(kp.counters + 2, (unsigned long long)ncalls_total);
             atomicAdd(kp.counters + 3, (unsigned long long)fast_calls);

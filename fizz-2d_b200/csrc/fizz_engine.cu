@@ -221,6 +221,7 @@ int fizz_layout(const FizzGroupDesc *d, int64_t n_worlds, FizzLayout *out) {
     L.steps = o; o += Wp;
     L.calls = o; o += Wp;
     L.vflag = o; o += Wp;
+    L.tier = o; o += Wp;
     L.state_words = o;
     L.off = o; o += 2 * (int64_t)V * Wp;
     L.thr = o; o += F * Wp;
@@ -265,6 +266,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     kp.pos = s + L.pos; kp.vel = s + L.vel; kp.heat = s + L.heat;
     kp.status = (long long *)(s + L.status); kp.steps = (long long *)(s + L.steps);
     kp.calls = (long long *)(s + L.calls); kp.vflag = (long long *)(s + L.vflag);
+    kp.tier = (long long *)(s + L.tier);
     kp.off = s + L.off; kp.thr = s + L.thr; kp.mass = s + L.mass; kp.verts = s + L.verts;
     g->sched_list = (long long *)(s + L.sched);
     g->sched_count = (unsigned long long *)(s + L.sched + L.stride);
@@ -463,7 +465,10 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         g->target += c;
         kp.target_steps = g->target;
         cudaEvent_t ea = g->profile ? next_event(g, st) : nullptr;
-        FIZZ_DISPATCH_F(F, (ballistic_kernel<FF><<<bgrid, BALLISTIC_BLOCK, 0, st>>>(kp)));
+        // live list: running worlds that are not flagged "in a contact phase" (a performance hint only)
+        CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
+        live_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, g->sched_list, g->sched_count);
+        FIZZ_DISPATCH_F(F, (ballistic_kernel<FF><<<bgrid, BALLISTIC_BLOCK, 0, st>>>(kp, g->sched_list, g->sched_count)));
         cudaEvent_t eb = g->profile ? next_event(g, st) : nullptr;
         CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
         classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, W, g->target, g->sched_list, g->sched_count);
@@ -474,7 +479,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             g->spans.push_back({FIZZ_KERNEL_CONTACT, eb, next_event(g, st)});
         }
         CU(cudaGetLastError());
-        g->launches += 3;
+        g->launches += 4;
         done += c;
     }
     return FIZZ_OK;

@@ -34,7 +34,7 @@ class FizzGroupDesc(C.Structure):
 class FizzLayout(C.Structure):
     _fields_ = [("n_worlds", C.c_int64), ("stride", C.c_int64),
                 ("n_free", C.c_int32), ("n_fixed", C.c_int32), ("n_free_verts", C.c_int32), ("reserved", C.c_int32)] + \
-               [(n, C.c_int64) for n in ("pos", "vel", "heat", "status", "steps", "calls", "vflag", "state_words",
+               [(n, C.c_int64) for n in ("pos", "vel", "heat", "status", "steps", "calls", "vflag", "tier", "state_words",
                                          "off", "thr", "mass", "verts", "energy", "sched", "scene", "total_words")]
 
 

@@ -95,7 +95,8 @@ typedef struct FizzLayout {
     int64_t steps;      /* [1]   int64 completed update() calls                        */
     int64_t calls;      /* [1]   int64 state-relevant check_collisions() calls, lifetime */
     int64_t vflag;      /* [1]   int64 1 = `verts` holds explicit point.pos (pushed by a resolve pass), 0 = derived */
-    int64_t state_words;/* words from `pos` to the end of `vflag` */
+    int64_t tier;       /* [1]   int64 scheduling hint: 1 = world is in a contact phase (skip the ballistic kernel)       */
+    int64_t state_words;/* words from `pos` to the end of `tier` */
     /* per-world constants */
     int64_t off;        /* [V*2] |r|cos(phi), |r|sin(phi) per free vertex (physics.py:358-359,632-635) */
     int64_t thr;        /* [F]   T(obj.radius) per free body        (physics.py:322,277-278) */
