@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=256, help="timesteps per chunk (hybrid mode)")
     ap.add_argument("--mode", default="hybrid", choices=["hybrid", "thread"])
     ap.add_argument("--max-calls", type=int, default=4096)
-    ap.add_argument("--cpu-sample-worlds", type=int, default=4096)
+    ap.add_argument("--cpu-sample-worlds", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -84,7 +84,7 @@ def cpu_run(spec, worlds, timesteps, threads, max_calls):
 def build_spec(args, rank, world_size):
     import fizz2d_b200 as fz
     from fizz2d_b200.batch import GroupSpec
-    sc = fz.load_in(os.path.join(ROOT, "simulations", SCENE + ".in"))
+    sc = fz.load_in(fz.scenes.scene_path(SCENE))
     from fizz2d_b200 import distributed as fd
     total = args.worlds * world_size
     idx = fd.shard_indices(total, rank, world_size)          # interleaved: world w lives on rank w % G

@@ -2,8 +2,8 @@
 oracle/ref_harness.py) in the build container.  Re-run with:  python oracle/make_golden.py
 
 Outputs (all small, committed):
-  simulations/<SCENE>.in                the reference's scene INPUT files (data, not code), so that tests, smoke()
-                                        and bench.py can run where /root/reference does not exist
+  (each <SCENE>.npz carries the scene's input text in `scene_text`; fizz2d_b200.scenes materialises
+   simulations/<SCENE>.in from it on demand, so tests, smoke() and bench.py run where /root/reference is absent)
   tests/golden/<SCENE>.npz              unperturbed scene, per-step full-precision trace
   tests/golden/perturbed_<NAME>.npz     perturbed worlds (SURVEY 8d law), checkpoints + contact traces
   tests/golden/anchors.json             1000-step sha256 anchors, regenerated here
@@ -193,10 +193,6 @@ def gen_anchors():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    os.makedirs(os.path.join(ROOT, "simulations"), exist_ok=True)
-    for name in SCENES:
-        with open(scene_path(name)) as f, open(os.path.join(ROOT, "simulations", name + ".in"), "w") as g:
-            g.write(f.read())
     for name in SCENES:
         gen_scene(name, 320)
     # gravity extension (reachable only through the Python API in the reference)

@@ -31,4 +31,5 @@ def golden(name):
 
 
 def scene_file(name):
-    return os.path.join(SCENES_DIR, name + ".in")
+    from fizz2d_b200 import scenes
+    return scenes.scene_path(name)

@@ -28,7 +28,7 @@ def _results_for(indices, n_total, steps):
     import fizz2d_b200 as fz
     from fizz2d_b200.batch import GroupSpec
     from helpers import oracle_from_spec
-    sc = fz.load_in(os.path.join(ROOT, "simulations", "2CHAMBERS_3BALLS.in"))
+    sc = fz.load_in(fz.scenes.scene_path("2CHAMBERS_3BALLS"))
     deltas = fz.perturbation_deltas(20260004, n_total, sc.n_free)[indices]
     spec = GroupSpec.from_scene(sc, len(indices), np.ascontiguousarray(deltas), max_calls=128)
     rows = np.zeros((6, len(indices)))

@@ -7,7 +7,7 @@ import fizz2d_b200 as fz
 from fizz2d_b200.batch import GroupSpec
 wi = int(sys.argv[1]) if len(sys.argv) > 1 else 103
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-sc = fz.load_in("simulations/RAMPWORLD_2TRIANGLES_5SQUARES.in")
+sc = fz.load_in(fz.scenes.scene_path("RAMPWORLD_2TRIANGLES_5SQUARES"))
 d = fz.perturbation_deltas(20260003, 65536, 7)[[wi]]
 bw = fz.BatchedWorld([GroupSpec.from_scene(sc, 1, np.ascontiguousarray(d))])
 bw.set_tuning("hybrid", 256)

@@ -12,7 +12,7 @@ from fizz2d_b200.batch import GroupSpec
 
 worlds = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "103,532,1555,1188").split(",")]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-sc = fz.load_in("simulations/RAMPWORLD_2TRIANGLES_5SQUARES.in")
+sc = fz.load_in(fz.scenes.scene_path("RAMPWORLD_2TRIANGLES_5SQUARES"))
 d = fz.perturbation_deltas(20260003, 65536, 7)[worlds]
 for mode in ("hybrid", "thread"):
     for sel in ([0], list(range(len(worlds)))):

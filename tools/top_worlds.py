@@ -2,7 +2,7 @@ import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import fizz2d_b200 as fz
-bw = fz.BatchedWorld.from_in("simulations/RAMPWORLD_2TRIANGLES_5SQUARES.in", n_worlds=65536, perturb=True, seed=20260003)
+bw = fz.BatchedWorld.from_in(fz.scenes.scene_path("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=65536, perturb=True, seed=20260003)
 bw.step(1000)
 c = bw.calls(); st = bw.status(); sd = bw.steps_done()
 o = np.argsort(-c)
