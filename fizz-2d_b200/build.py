@@ -27,7 +27,8 @@ def needs_build():
 def build_extension(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
+    extra = os.environ.get("FIZZ_NVCC_EXTRA", "").split()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
     subprocess.check_call(cmd)
     return OUT
 
