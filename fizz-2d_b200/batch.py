@@ -248,6 +248,23 @@ class BatchedWorld:
             _lib.check(L.fizz_step(g.handle, int(n_steps), C.c_void_p(self._stream_ptr(k))))
         self.steps_requested += int(n_steps)
 
+    def step_logged(self, n_steps):
+        """n_steps x update() with the energy row of EVERY world recorded before each step (the batched energy.txt).
+        Returns a float64 array (n_steps, W, 4): total, kinetic, potential, heat."""
+        import torch
+        L = _lib.load()
+        logs = []
+        for k, g in enumerate(self.groups):
+            t = torch.empty((int(n_steps), 4, g.layout.stride), dtype=torch.float64, device=g.slab.device)
+            _lib.check(L.fizz_step_logged(g.handle, int(n_steps), C.c_void_p(t.data_ptr()), C.c_void_p(self._stream_ptr(k))))
+            logs.append(t)
+        self.steps_requested += int(n_steps)
+        self.synchronize()
+        out = np.empty((int(n_steps), self.n_worlds, 4))
+        for g, t in zip(self.groups, logs):
+            out[:, g.world_ids, :] = t[:, :, :g.spec.n_worlds].permute(0, 2, 1).cpu().numpy()
+        return out
+
     def synchronize(self):
         import torch
         torch.cuda.synchronize(self.device)

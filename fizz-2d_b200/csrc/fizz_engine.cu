@@ -501,6 +501,33 @@ int fizz_energy(FizzGroup *g, void *stream) {
     return FIZZ_OK;
 }
 
+int fizz_step_logged(FizzGroup *g, int64_t n_steps, double *dev_energy_log, void *stream) {
+    if (!g || !dev_energy_log) return fail(FIZZ_E_ARG, "fizz_step_logged: null argument");
+    if (!g->uploaded) return fail(FIZZ_E_STATE, "fizz_step_logged: call fizz_upload first");
+    if (n_steps < 0) return fail(FIZZ_E_ARG, "fizz_step_logged: n_steps < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(g->device));
+    const FizzLayout &L = g->lay;
+    double *s = g->slab;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((L.n_worlds + threads - 1) / threads);
+    const long long saved_chunk = g->chunk;
+    g->chunk = 1;
+    int rc = FIZZ_OK;
+    for (int64_t t = 0; t < n_steps && rc == FIZZ_OK; t++) {
+        // the row main.py would append to energy.txt BEFORE update() number t (physics.py:81-82), for every world
+        energy_kernel<<<blocks, threads, 0, st>>>(s + L.pos, s + L.vel, s + L.heat, s + L.mass,
+                                                  dev_energy_log + (size_t)t * 4 * L.stride, L.n_worlds, L.stride, L.n_free,
+                                                  g->prm.gy, g->prm.height);
+        g->launches++;
+        rc = fizz_step(g, 1, stream);
+    }
+    g->chunk = saved_chunk;
+    if (rc != FIZZ_OK) return rc;
+    CU(cudaGetLastError());
+    return FIZZ_OK;
+}
+
 int fizz_vertices(FizzGroup *g, void *stream) {
     if (!g) return fail(FIZZ_E_ARG, "fizz_vertices: null group");
     if (!g->uploaded) return fail(FIZZ_E_STATE, "fizz_vertices: call fizz_upload first");

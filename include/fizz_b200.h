@@ -154,6 +154,11 @@ int fizz_upload(FizzGroup *g, const double *pos, const double *vel, const double
  * launch and one persistent contact launch (warp per world).  Thread mode: one launch for all n_steps. */
 int fizz_step(FizzGroup *g, int64_t n_steps, void *stream);
 
+/* Streaming variant: like fizz_step, but before every timestep t the World.energy() row of EVERY world
+ * -- what main.py appends to energy.txt (physics.py:81-82) -- is written to dev_energy_log[t][4][Wp] (device memory,
+ * n_steps * 4 * layout.stride doubles).  One launch set per timestep; HBM-bound output of 32 B per world-step. */
+int fizz_step_logged(FizzGroup *g, int64_t n_steps, double *dev_energy_log, void *stream);
+
 /* Execution mode and timesteps per chunk (hybrid mode).  Results never depend on either. */
 int fizz_set_tuning(FizzGroup *g, int32_t mode, int64_t chunk_steps);
 

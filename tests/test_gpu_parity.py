@@ -230,3 +230,18 @@ def test_hybrid_equals_thread_mode_large_batch():
         outs.append((bw.com(), bw.heat(), bw.status(), bw.steps_done(), bw.calls(), bw.vertices()))
     for x, y in zip(*outs):
         assert np.array_equal(bits(x) if x.dtype == np.float64 else x, bits(y) if y.dtype == np.float64 else y)
+
+
+def test_batched_energy_log_equals_reference_rows():
+    """step_logged: the per-step energy rows of every world; world 0 reproduces the reference's energy.txt."""
+    g = golden("BOX_1SQUAREFRICTION")
+    bw = fz.BatchedWorld.from_in(scene_file("BOX_1SQUAREFRICTION"), n_worlds=200, perturb=True, seed=20260002)
+    n = int(g["steps_done"])
+    log = bw.step_logged(n)
+    assert log.shape == (n, 200, 4)
+    assert np.array_equal(bits(log[:, 0, :]), bits(g["energy_before"]))
+    assert np.array_equal(bits(bw.com()[0]), bits(g["com"][n - 1]))
+    # conservation for every uncapped world, every step
+    ok = bw.status() == 0
+    rel = np.abs(log[:, ok, 0] - log[0, ok, 0]) / log[0, ok, 0]
+    assert rel.max() < 1e-12
