@@ -84,3 +84,38 @@ def fixed_scene_text(scene: _scene.Scene):
     for k, v in scene.params.items():
         out += "PARAM %s %r\n" % (k, v)
     return out
+
+
+def next_generation(population, fitness, seed, generation, survivors=0.25, sigma=0.6, center=(112.5, 290.0), eps=1e-12):
+    """One GA generation step on the host: keep the `survivors` fraction with the highest fitness,
+    refill the population with mutated copies (every vertex jittered by N(0, sigma) px, velocity by N(0, 3 sigma)),
+    re-sorted by polar angle about the centroid so the polygon stays simple; candidates that are not strictly
+    convex or that the reference cannot simulate are redrawn.  Deterministic in (seed, generation).
+    population = (nverts, points, velocity) as returned by random_convex_polygons; returns the same triple."""
+    nverts, pts, vel = population
+    W = len(pts)
+    order = np.argsort(-np.asarray(fitness), kind="stable")
+    keep = order[:max(1, int(round(W * survivors)))]
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence([seed, 1000003, generation])))
+    new_n = np.empty(W, dtype=np.int64)
+    new_pts = [None] * W
+    new_vel = np.empty((W, 2))
+    for slot in range(W):
+        if slot < len(keep):
+            w = keep[slot]
+            new_n[slot], new_pts[slot], new_vel[slot] = nverts[w], pts[w], vel[w]
+            continue
+        parent = keep[rng.integers(0, len(keep))]
+        for _ in range(64):
+            P = pts[parent] + rng.normal(0.0, sigma, pts[parent].shape)
+            c = P.mean(axis=0)
+            P = P[np.argsort(np.arctan2(P[:, 1] - c[1], P[:, 0] - c[0]))]
+            e = np.roll(P, -1, axis=0) - P
+            cross = e[:, 0] * np.roll(e, -1, axis=0)[:, 1] - e[:, 1] * np.roll(e, -1, axis=0)[:, 0]
+            if (cross > 1e-6).all() and bool(_scene.polygon_constants(P[None], np.ones(1), eps)["valid"][0]):
+                break
+        else:
+            P = pts[parent]
+        new_n[slot], new_pts[slot] = len(P), P
+        new_vel[slot] = vel[parent] + rng.normal(0.0, 3 * sigma, 2)
+    return new_n, new_pts, new_vel

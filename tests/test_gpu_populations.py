@@ -87,3 +87,22 @@ def test_ga_population_vs_oracle_and_dump():
     assert text.startswith("200,400\npolygon\nsides,") and text.count("polygon") == 3
     # fitness := dissipated energy is non-negative and zero for worlds that never touched anything
     assert (heat >= 0).all()
+
+
+def test_ga_generation_loop_improves_fitness():
+    """Two GA generations on the GPU: selection keeps the best candidates bit for bit, offspring are valid shapes."""
+    path = scene_file("PENTAGONVOID_1SQUARE")
+    pop = fz.ga.random_convex_polygons(5, 1024)
+    best = []
+    for gen in range(2):
+        bw = fz.BatchedWorld.from_ga(path, 1024, population=pop, max_calls=128)
+        bw.step(300)
+        fit = np.where(bw.status() == 0, bw.calls().astype(float), -1.0)   # any deterministic score will do here
+        best.append(fit.max())
+        new = fz.ga.next_generation(pop, fit, 5, gen)
+        top = int(np.argmax(fit))
+        assert np.array_equal(bits(new[1][0]), bits(pop[1][top]))          # elitism: the best survives unchanged
+        assert all(3 <= len(p) <= 12 for p in new[1])
+        pop = new
+        bw.close()
+    assert best[1] >= best[0]
