@@ -397,8 +397,9 @@ class BatchedWorld:
 
     def set_tuning(self, mode="hybrid", chunk_steps=256):
         """Execution strategy (results never depend on it): "hybrid" = ballistic thread-per-world kernel +
-        warp-per-world contact kernel per chunk of timesteps; "thread" = one thread-per-world kernel."""
-        m = {"hybrid": _lib.MODE_HYBRID, "thread": _lib.MODE_THREAD}[mode]
+        warp-per-world contact kernel per chunk of timesteps; "hybrid3" = the same plus a thread-per-world separation
+        prover tier (busy scenes, use small chunks); "thread" = one thread-per-world kernel."""
+        m = {"hybrid": _lib.MODE_HYBRID, "thread": _lib.MODE_THREAD, "hybrid3": _lib.MODE_HYBRID3}[mode]
         for g in self.groups:
             _lib.check(_lib.load().fizz_set_tuning(g.handle, m, int(chunk_steps)))
 
@@ -448,7 +449,7 @@ class BatchedWorld:
         for g in self.groups:
             d = {}
             for name, which in (("thread", _lib.KERNEL_THREAD), ("ballistic", _lib.KERNEL_BALLISTIC),
-                                ("contact", _lib.KERNEL_CONTACT)):
+                                ("prover", _lib.KERNEL_PROVER), ("contact", _lib.KERNEL_CONTACT)):
                 r, s, t, b = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
                 n = C.c_int64()
                 _lib.check(_lib.load().fizz_kernel_info(g.handle, which, C.byref(r), C.byref(s), C.byref(t), C.byref(b),

@@ -458,7 +458,8 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 
         bool resolve = false, verts_explicit = false;
         int k = 0, ncalls = 0, ns = 0;
-        int quiet = 0;  // consecutive timesteps with an empty broad phase (scheduling hint only)
+        int quiet = 0;        // consecutive contact-free timesteps: one check_collisions(), no tuple (scheduling hint)
+        int quiet_empty = 0;  // ... of those, consecutive ones whose broad phase was empty
         double dt = kp.time_disc;
 
         while (true) {
@@ -723,7 +724,8 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             if (lane < F) { s.sx[lane] = s.px[lane]; s.sy[lane] = s.py[lane]; }  // finish_update (:237-239, :251)
             __syncwarp();
             step++;                                            // :259
-            quiet = (ncalls == 1 && ns == 0) ? quiet + 1 : 0;
+            quiet = (ncalls == 1) ? quiet + 1 : 0;  // (a step with a tuple makes at least two calls)
+            quiet_empty = (ncalls == 1 && ns == 0) ? quiet_empty + 1 : 0;
             resolve = false; k = 0; dt = kp.time_disc; ncalls = 0;
             if (step >= kp.target_steps) break;
             verts_explicit = false;
@@ -750,7 +752,9 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             kp.steps[w] = step;
             kp.calls[w] += ncalls_total;
             kp.vflag[w] = verts_explicit ? 1 : 0;
-            kp.tier[w] = (quiet >= 8) ? 0 : 1;  // back to the ballistic kernel after 8 quiescent steps
+            // hint for the next chunk: 0 quiescent (lean thread-per-world kernel), 1 candidates but no contact (prover
+            // variant, when enabled), 2 contact phase (stay here)
+            kp.tier[w] = (quiet_empty >= 8) ? 0 : ((quiet >= 2) ? 1 : 2);
             atomicAdd(kp.counters + 1, (unsigned long long)(step - step_in));
             atomicAdd(kp.counters + 2, (unsigned long long)ncalls_total);
             atomicAdd(kp.counters + 3, (unsigned long long)fast_calls);

@@ -103,10 +103,18 @@ cudaError_t prep_thread(size_t smem, KernelInfo *ki) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, step_kernel<F>, BLOCK, smem);
 }
 template <int F>
-cudaError_t prep_ballistic(KernelInfo *ki) {
-    cudaError_t e = cudaFuncGetAttributes(&ki->attr, ballistic_kernel<F>);
+cudaError_t prep_ballistic(size_t smem, KernelInfo *ki, KernelInfo *kp_prover) {
+    static size_t current = 0;
+    cudaError_t e = raise_dynamic_smem(ballistic_kernel<F, true>, smem, &current);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, ballistic_kernel<F>, BALLISTIC_BLOCK, 0);
+    e = cudaFuncGetAttributes(&ki->attr, ballistic_kernel<F, false>);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, ballistic_kernel<F, false>, BALLISTIC_BLOCK, 0);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&kp_prover->attr, ballistic_kernel<F, true>);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kp_prover->blocks_per_sm, ballistic_kernel<F, true>,
+                                                         BALLISTIC_BLOCK, smem);
 }
 
 #define FIZZ_DISPATCH_F(F_, CALL)          \
@@ -145,8 +153,8 @@ struct FizzGroup {
     KernelInfo thread_ki;
     bool thread_ok;
     // hybrid mode
-    KernelInfo ballistic_ki, contact_ki;
-    size_t contact_smem;
+    KernelInfo ballistic_ki, prover_ki, contact_ki;
+    size_t contact_smem, ballistic_smem;
     long long *sched_list;
     unsigned long long *sched_count;  // [0] = count, [1] = cursor
     unsigned char *vbody_dev;
@@ -327,7 +335,8 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     g->thread_ok = (e == cudaSuccess);
     if (!g->thread_ok) (void)cudaGetLastError();
     // hybrid mode
-    FIZZ_DISPATCH_F(F, e = prep_ballistic<FF>(&g->ballistic_ki));
+    g->ballistic_smem = ballistic_smem_bytes(F, kp.V, kp.FV);
+    FIZZ_DISPATCH_F(F, e = prep_ballistic<FF>(g->ballistic_smem, &g->ballistic_ki, &g->prover_ki));
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "ballistic kernel setup"); }
     g->contact_smem = contact_smem_bytes(kp.V, kp.FV);
     {
@@ -376,7 +385,8 @@ int fizz_profile_read(FizzGroup *g, double *ms, int64_t *launches, int32_t reset
 
 int fizz_set_tuning(FizzGroup *g, int32_t mode, int64_t chunk_steps) {
     if (!g) return fail(FIZZ_E_ARG, "fizz_set_tuning: null group");
-    if (mode != FIZZ_MODE_HYBRID && mode != FIZZ_MODE_THREAD) return fail(FIZZ_E_ARG, "fizz_set_tuning: unknown mode");
+    if (mode != FIZZ_MODE_HYBRID && mode != FIZZ_MODE_THREAD && mode != FIZZ_MODE_HYBRID3)
+        return fail(FIZZ_E_ARG, "fizz_set_tuning: unknown mode");
     if (mode == FIZZ_MODE_THREAD && !g->thread_ok)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: thread mode does not fit in shared memory for this topology");
     if (chunk_steps < 1) return fail(FIZZ_E_ARG, "fizz_set_tuning: chunk_steps must be >= 1");
@@ -459,16 +469,25 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     const long long W = g->lay.n_worlds;
     const dim3 bgrid((unsigned)((W + BALLISTIC_BLOCK - 1) / BALLISTIC_BLOCK));
     const dim3 cgrid((unsigned)((W + 255) / 256));
-    const dim3 kgrid((unsigned)(g->sm_count * g->contact_ki.blocks_per_sm));
+    // persistent grid: one CTA slot per resident block, but never more warps than worlds
+    const long long kfull = (long long)g->sm_count * g->contact_ki.blocks_per_sm, kneed = (W + CONTACT_WARPS - 1) / CONTACT_WARPS;
+    const dim3 kgrid((unsigned)(kneed < kfull ? kneed : kfull));
     for (int64_t done = 0; done < n_steps;) {
         const int64_t c = (n_steps - done < g->chunk) ? (n_steps - done) : g->chunk;
         g->target += c;
         kp.target_steps = g->target;
         cudaEvent_t ea = g->profile ? next_event(g, st) : nullptr;
-        // live list: running worlds that are not flagged "in a contact phase" (a performance hint only)
+        // tier 0 (quiescent worlds): lean registers-only variant; then tiers 0..1 (what is left + worlds with broad-phase
+        // candidates): prover variant.  The tier is a performance hint only; every kernel re-derives what it needs.
         CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
-        live_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, g->sched_list, g->sched_count);
-        FIZZ_DISPATCH_F(F, (ballistic_kernel<FF><<<bgrid, BALLISTIC_BLOCK, 0, st>>>(kp, g->sched_list, g->sched_count)));
+        live_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, g->sched_list, g->sched_count);
+        FIZZ_DISPATCH_F(F, (ballistic_kernel<FF, false><<<bgrid, BALLISTIC_BLOCK, 0, st>>>(kp, g->sched_list, g->sched_count)));
+        if (g->mode == FIZZ_MODE_HYBRID3) {
+            CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
+            live_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 1, g->sched_list, g->sched_count);
+            FIZZ_DISPATCH_F(F, (ballistic_kernel<FF, true><<<bgrid, BALLISTIC_BLOCK, g->ballistic_smem, st>>>(kp, g->sched_list, g->sched_count)));
+            g->launches += 2;
+        }
         cudaEvent_t eb = g->profile ? next_event(g, st) : nullptr;
         CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
         classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, W, g->target, g->sched_list, g->sched_count);
@@ -596,6 +615,7 @@ int fizz_kernel_info(FizzGroup *g, int32_t which, int32_t *regs, int32_t *smem, 
     switch (which) {
         case FIZZ_KERNEL_THREAD: ki = &g->thread_ki; th = BLOCK; sm = g->thread_smem; break;
         case FIZZ_KERNEL_BALLISTIC: ki = &g->ballistic_ki; th = BALLISTIC_BLOCK; sm = 0; break;
+        case FIZZ_KERNEL_PROVER: ki = &g->prover_ki; th = BALLISTIC_BLOCK; sm = g->ballistic_smem; break;
         case FIZZ_KERNEL_CONTACT: ki = &g->contact_ki; th = CONTACT_BLOCK; sm = g->contact_smem; break;
         default: return fail(FIZZ_E_ARG, "fizz_kernel_info: unknown kernel id");
     }

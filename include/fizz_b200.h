@@ -38,10 +38,13 @@ extern "C" {
 /* execution modes (fizz_set_tuning) */
 #define FIZZ_MODE_HYBRID 1  /* ballistic thread-per-world kernel + warp-per-world contact kernel (default) */
 #define FIZZ_MODE_THREAD 0  /* one thread-per-world kernel with the full semantics                        */
+#define FIZZ_MODE_HYBRID3 2 /* hybrid + a thread-per-world "separation prover" tier between the two: best for busy
+                               scenes (bodies always near fixed geometry) with small chunks (e.g. 32)            */
 /* kernel ids (fizz_kernel_info) */
 #define FIZZ_KERNEL_THREAD 0
 #define FIZZ_KERNEL_BALLISTIC 1
 #define FIZZ_KERNEL_CONTACT 2
+#define FIZZ_KERNEL_PROVER 3
 
 /* per-world status word (slab section `status`) */
 #define FIZZ_ST_RUNNING 0
@@ -95,7 +98,7 @@ typedef struct FizzLayout {
     int64_t steps;      /* [1]   int64 completed update() calls                        */
     int64_t calls;      /* [1]   int64 state-relevant check_collisions() calls, lifetime */
     int64_t vflag;      /* [1]   int64 1 = `verts` holds explicit point.pos (pushed by a resolve pass), 0 = derived */
-    int64_t tier;       /* [1]   int64 scheduling hint: 1 = world is in a contact phase (skip the ballistic kernel)       */
+    int64_t tier;       /* [1]   int64 scheduling hint: 0 quiescent, 1 broad-phase candidates but no contact, 2 contact phase */
     int64_t state_words;/* words from `pos` to the end of `tier` */
     /* per-world constants */
     int64_t off;        /* [V*2] |r|cos(phi), |r|sin(phi) per free vertex (physics.py:358-359,632-635) */

@@ -54,7 +54,7 @@ def random_scene(seed):
     return out, gravity
 
 
-@pytest.mark.parametrize("mode", [("hybrid", 37), ("thread", 1)], ids=["hybrid", "thread"])
+@pytest.mark.parametrize("mode", [("hybrid", 37), ("hybrid3", 16), ("thread", 1)], ids=["hybrid", "hybrid3", "thread"])
 @pytest.mark.parametrize("seed", list(range(24)))
 def test_random_scene_vs_oracle(seed, mode):
     text, gravity = random_scene(1000 + seed)

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 # execution strategies (results must never depend on them): hybrid = ballistic thread-per-world kernel + warp-per-
 # world contact kernel per chunk of timesteps; thread = one thread-per-world kernel with the full semantics
-MODES = [("hybrid", 256), ("hybrid", 7), ("thread", 1)]
+MODES = [("hybrid", 256), ("hybrid3", 7), ("thread", 1)]
 
 
 def tune(bw, mode):
@@ -46,7 +46,7 @@ def test_single_world_per_step_trace(name, mode):
     assert np.array_equal(bits([c[4:] for c in got]), bits([c[4:] for c in want]))
 
 
-@pytest.mark.parametrize("mode", MODES, ids=["hybrid256", "hybrid7", "thread"])
+@pytest.mark.parametrize("mode", MODES, ids=["hybrid256", "hybrid3-7", "thread"])
 @pytest.mark.parametrize("name", SCENES)
 @pytest.mark.parametrize("chunks", [(320,), (1, 7, 100, 212)])
 def test_fused_steps_equal_stepwise(name, chunks, mode):
@@ -85,7 +85,7 @@ def test_1000_step_anchors_through_text_formats(name):
     assert np.array_equal(bits(bw.com()[0]), bits(anchors["final_com"]))
 
 
-@pytest.mark.parametrize("mode", MODES, ids=["hybrid256", "hybrid7", "thread"])
+@pytest.mark.parametrize("mode", MODES, ids=["hybrid256", "hybrid3-7", "thread"])
 @pytest.mark.parametrize("tag,seed,nw,fmax", [("config2_boxfriction", 20260002, 4096, 1),
                                              ("config3_rampworld", 20260003, 65536, 7),
                                              ("config4_mixed", 20260004, 262144, 3)])
@@ -128,7 +128,7 @@ def test_perturbed_worlds_match_reference(tag, seed, nw, fmax, mode):
             assert np.array_equal(bits([c[4:] for c in got]), bits([c[4:] for c in want]))
 
 
-@pytest.mark.parametrize("mode", [("hybrid", 50), ("thread", 1)], ids=["hybrid50", "thread"])
+@pytest.mark.parametrize("mode", [("hybrid", 50), ("hybrid3", 32), ("thread", 1)], ids=["hybrid50", "hybrid3-32", "thread"])
 @pytest.mark.parametrize("name,seed,n,steps,mc", [("BOX_1SQUAREFRICTION", 20260002, 4096, 400, 4096),
                                                    ("RAMPWORLD_2TRIANGLES_5SQUARES", 20260003, 1024, 400, 256),
                                                    ("2CHAMBERS_3BALLS", 20260004, 1024, 300, 256),
@@ -223,13 +223,14 @@ def test_snapshot_restore_replays_bit_exactly():
 def test_hybrid_equals_thread_mode_large_batch():
     """The two independent kernel families agree bit for bit on 8192 perturbed RAMPWORLD worlds x 600 steps."""
     outs = []
-    for mode in (("hybrid", 128), ("thread", 1)):
+    for mode in (("hybrid", 128), ("hybrid3", 32), ("thread", 1)):
         bw = tune(fz.BatchedWorld.from_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=8192, perturb=True,
                                           seed=20260003, max_calls=128), mode)
         bw.step(600)
         outs.append((bw.com(), bw.heat(), bw.status(), bw.steps_done(), bw.calls(), bw.vertices()))
-    for x, y in zip(*outs):
-        assert np.array_equal(bits(x) if x.dtype == np.float64 else x, bits(y) if y.dtype == np.float64 else y)
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert np.array_equal(bits(x) if x.dtype == np.float64 else x, bits(y) if y.dtype == np.float64 else y)
 
 
 def test_batched_energy_log_equals_reference_rows():

@@ -10,10 +10,10 @@ from conftest import golden, scene_file
 from helpers import bits, contact_rows, oracle_from_spec, orc
 
 pytestmark = pytest.mark.gpu
-MODES = [("hybrid", 64), ("thread", 1)]
+MODES = [("hybrid", 64), ("hybrid3", 32), ("thread", 1)]
 
 
-@pytest.mark.parametrize("mode", MODES, ids=["hybrid", "thread"])
+@pytest.mark.parametrize("mode", MODES, ids=["hybrid", "hybrid3", "thread"])
 def test_mixed_batch_matches_reference(mode):
     """Worlds 0..12 of config 4 (even: 2CHAMBERS_3BALLS, odd: STACKEDCHAMBERS_1SQUARE, seed 20260004)."""
     g = golden("perturbed_config4_mixed")
@@ -34,7 +34,7 @@ def test_mixed_batch_matches_reference(mode):
             assert np.array_equal(bits(en[wi]), bits(g[pre + "final_energy"]))
 
 
-@pytest.mark.parametrize("mode", MODES, ids=["hybrid", "thread"])
+@pytest.mark.parametrize("mode", MODES, ids=["hybrid", "hybrid3", "thread"])
 def test_ga_population_matches_reference(mode):
     g = golden("ga_config5_pentagonvoid")
     n = int(g["worlds"].max()) + 1
