@@ -449,7 +449,8 @@ class BatchedWorld:
         for g in self.groups:
             d = {}
             for name, which in (("thread", _lib.KERNEL_THREAD), ("ballistic", _lib.KERNEL_BALLISTIC),
-                                ("prover", _lib.KERNEL_PROVER), ("contact", _lib.KERNEL_CONTACT)):
+                                ("prover", _lib.KERNEL_PROVER), ("contact", _lib.KERNEL_CONTACT),
+                                ("trapped", _lib.KERNEL_TRAPPED)):
                 r, s, t, b = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
                 n = C.c_int64()
                 _lib.check(_lib.load().fizz_kernel_info(g.handle, which, C.byref(r), C.byref(s), C.byref(t), C.byref(b),

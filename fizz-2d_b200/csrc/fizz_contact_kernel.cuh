@@ -389,7 +389,15 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(CONTACT_BLOCK, 3)
+// Two instances of the same kernel, tuned for the two regimes of a batch:
+// FAST = false: the GENERAL instance -- compact narrow phase (one item per lane and round, smaller instruction
+//   footprint), 128 registers / 4 CTAs per SM: it owns the throughput phase (most worlds, short contact episodes).
+//   A world whose timestep spent >= 32 calls in the single-contact fast path is flagged tier 3 ("trapped"): from the
+//   next chunk on the other instance steps it.
+// FAST = true : the TRAPPED instance -- two narrow-phase items per lane for ILP, 168 registers / 3 CTAs per SM: it owns
+//   the latency-bound tail (tier 3 worlds) and hands a world back after 8 calm timesteps.
+template <bool FAST>
+__global__ void __launch_bounds__(CONTACT_BLOCK, FAST ? 3 : 4)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
                const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor) {
     extern __shared__ double smem_c[];
@@ -458,6 +466,8 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 
         bool resolve = false, verts_explicit = false;
         int k = 0, ncalls = 0, ns = 0;
+        int fast_step = 0, calm = 0;  // tier-3 bookkeeping (scheduling hint only)
+        bool trapped = false;
         int quiet = 0;        // consecutive contact-free timesteps: one check_collisions(), no tuple (scheduling hint)
         int quiet_empty = 0;  // ... of those, consecutive ones whose broad phase was empty
         double dt = kp.time_disc;
@@ -521,31 +531,82 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     __syncwarp();
                 }
                 // ---- narrow phase: (pair, axis) items in SW-wide slots, two sets of PR pairs per round ------------
-                for (int p0 = 0; p0 < ns; p0 += 2 * PR) {
-                    const int pa = p0 + my_slot, pb = p0 + PR + my_slot;
-                    pairmeta_t ma = 0, mb = 0;
-                    double nxa = 0.0, nya = 0.0, cura = INFINITY, nxb = 0.0, nyb = 0.0, curb = INFINITY;
-                    bool sepa = false, sepb = false, acta = false, actb = false;
-                    if (pa < ns) {
-                        ma = s.sp[pa];
-                        acta = my_k < PM_N1(ma) + PM_N2(ma);
+                if constexpr (FAST) {
+                    for (int p0 = 0; p0 < ns; p0 += 2 * PR) {
+                        const int pa = p0 + my_slot, pb = p0 + PR + my_slot;
+                        pairmeta_t ma = 0, mb = 0;
+                        double nxa = 0.0, nya = 0.0, cura = INFINITY, nxb = 0.0, nyb = 0.0, curb = INFINITY;
+                        bool sepa = false, sepb = false, acta = false, actb = false;
+                        if (pa < ns) {
+                            ma = s.sp[pa];
+                            acta = my_k < PM_N1(ma) + PM_N2(ma);
+                        }
+                        if (pb < ns) {
+                            mb = s.sp[pb];
+                            actb = my_k < PM_N1(mb) + PM_N2(mb);
+                        }
+                        if (acta) sat_axis(s, F, ma, my_k, nxa, nya, cura, sepa);
+                        if (actb) sat_axis(s, F, mb, my_k, nxb, nyb, curb, sepb);
+    #pragma unroll
+                        for (int set = 0; set < 2; set++) {
+                            const pairmeta_t m = set ? mb : ma;
+                            const bool act = set ? actb : acta, sep = set ? sepb : sepa;
+                            const double nx = set ? nxb : nxa, ny = set ? nyb : nya, cur = set ? curb : cura;
+                            const bool pair_live = (set ? pb : pa) < ns;
+                            if (set == 1 && p0 + PR >= ns) break;  // uniform
+                            const unsigned sepbits = __ballot_sync(FULL, sep);
+                            const bool pair_sep = (sepbits & slot_mask) != 0;
+                            // first strict minimum in axis order (:827-830) = lexicographic min of (overlap, axis)
+                            const bool valid = act && (cur < INFINITY);
+                            double bov = valid ? cur : INFINITY;
+                            int bk = valid ? my_k : 99;
+                            for (int o = 1; o < SW; o <<= 1) {
+                                const double oov = __shfl_xor_sync(FULL, bov, o);
+                                const int ok = __shfl_xor_sync(FULL, bk, o);
+                                if (oov < bov || (oov == bov && ok < bk)) { bov = oov; bk = ok; }
+                            }
+                            const int src = (my_slot * SW + (bk == 99 ? 0 : bk)) & 31;
+                            const double fxn = __shfl_sync(FULL, nx, src), fyn = __shfl_sync(FULL, ny, src);
+                            const bool hit = pair_live && (my_k == 0) && !pair_sep && (bk != 99);  // :286-288
+                            const unsigned hitb = __ballot_sync(FULL, hit);
+                            if (hitb) {
+                                if (hit) {
+                                    const int slot = nh + __popc(hitb & lt_mask);
+                                    const double hx = fxn * -1.0, hy = fyn * -1.0;  // :838-839 always negated (Q7)
+                                    const int ii = PM_II(m), jj = PM_JJ(m);
+                                    if (slot < FIZZ_MAX_HITS) {
+                                        s.hi[slot] = (unsigned char)ii; s.hj[slot] = (unsigned char)jj;
+                                        s.hnx[slot] = hx; s.hny[slot] = hy; s.hmag[slot] = bov;
+                                    }
+                                    if (kp.trace) trace_hit(kp, w, step, ncalls, ii, jj, hx, hy, bov);
+                                }
+                                nh += __popc(hitb);
+                                // max |overlap| over this set's hits: slot leaders hold them
+                                double am = hit ? fabs(bov) : -1.0;
+                                for (int o = SW; o < 32; o <<= 1) {
+                                    const double other = __shfl_xor_sync(FULL, am, o);
+                                    if (other > am) am = other;
+                                }
+                                am = __shfl_sync(FULL, am, 0);
+                                if (am > maxov) maxov = am;
+                            }
+                        }
                     }
-                    if (pb < ns) {
-                        mb = s.sp[pb];
-                        actb = my_k < PM_N1(mb) + PM_N2(mb);
-                    }
-                    if (acta) sat_axis(s, F, ma, my_k, nxa, nya, cura, sepa);
-                    if (actb) sat_axis(s, F, mb, my_k, nxb, nyb, curb, sepb);
-#pragma unroll
-                    for (int set = 0; set < 2; set++) {
-                        const pairmeta_t m = set ? mb : ma;
-                        const bool act = set ? actb : acta, sep = set ? sepb : sepa;
-                        const double nx = set ? nxb : nxa, ny = set ? nyb : nya, cur = set ? curb : cura;
-                        const bool pair_live = (set ? pb : pa) < ns;
-                        if (set == 1 && p0 + PR >= ns) break;  // uniform
+                } else {
+    #pragma unroll 1
+                    for (int p0 = 0; p0 < ns; p0 += PR) {
+                        const int pa = p0 + my_slot;
+                        pairmeta_t m = 0;
+                        double nx = 0.0, ny = 0.0, cur = INFINITY;
+                        bool sep = false, act = false;
+                        const bool pair_live = pa < ns;
+                        if (pair_live) {
+                            m = s.sp[pa];
+                            act = my_k < PM_N1(m) + PM_N2(m);
+                        }
+                        if (act) sat_axis(s, F, m, my_k, nx, ny, cur, sep);
                         const unsigned sepbits = __ballot_sync(FULL, sep);
                         const bool pair_sep = (sepbits & slot_mask) != 0;
-                        // first strict minimum in axis order (:827-830) = lexicographic min of (overlap, axis)
                         const bool valid = act && (cur < INFINITY);
                         double bov = valid ? cur : INFINITY;
                         int bk = valid ? my_k : 99;
@@ -570,7 +631,6 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                                 if (kp.trace) trace_hit(kp, w, step, ncalls, ii, jj, hx, hy, bov);
                             }
                             nh += __popc(hitb);
-                            // max |overlap| over this set's hits: slot leaders hold them
                             double am = hit ? fabs(bov) : -1.0;
                             for (int o = SW; o < 32; o <<= 1) {
                                 const double other = __shfl_xor_sync(FULL, am, o);
@@ -704,6 +764,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     else if (nb == 3) fast_resolve<3>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
                     else if (nb <= 8) fast_resolve<0>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
                     fast_calls += ncalls_total - before;
+                    fast_step += (int)(ncalls_total - before);
                 }
                 continue;
             }
@@ -727,6 +788,15 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             quiet = (ncalls == 1) ? quiet + 1 : 0;  // (a step with a tuple makes at least two calls)
             quiet_empty = (ncalls == 1 && ns == 0) ? quiet_empty + 1 : 0;
             resolve = false; k = 0; dt = kp.time_disc; ncalls = 0;
+            if constexpr (FAST) {
+                calm = (fast_step < 32) ? calm + 1 : 0;
+                fast_step = 0;
+            } else {
+                // a timestep with a long single-contact resolve loop: the latency-tuned instance takes the world
+                const bool heavy = fast_step >= 32;
+                fast_step = 0;
+                if (heavy) trapped = true;  // flagged for the NEXT chunk; this chunk is finished here (no idle time)
+            }
             if (step >= kp.target_steps) break;
             verts_explicit = false;
         }
@@ -754,7 +824,8 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             kp.vflag[w] = verts_explicit ? 1 : 0;
             // hint for the next chunk: 0 quiescent (lean thread-per-world kernel), 1 candidates but no contact (prover
             // variant, when enabled), 2 contact phase (stay here)
-            kp.tier[w] = (quiet_empty >= 8) ? 0 : ((quiet >= 2) ? 1 : 2);
+            const long long calm_tier = (quiet_empty >= 8) ? 0 : ((quiet >= 2) ? 1 : 2);
+            kp.tier[w] = FAST ? ((calm >= 8) ? calm_tier : 3) : (trapped ? 3 : calm_tier);
             atomicAdd(kp.counters + 1, (unsigned long long)(step - step_in));
             atomicAdd(kp.counters + 2, (unsigned long long)ncalls_total);
             atomicAdd(kp.counters + 3, (unsigned long long)fast_calls);
@@ -764,10 +835,11 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 }
 
 // Work list for the contact kernel: every running world that has not reached the chunk target.
-__global__ void classify_kernel(const long long *status, const long long *steps, long long W, long long target,
-                                long long *list, unsigned long long *count) {
+__global__ void classify_kernel(const long long *status, const long long *steps, const long long *tier, long long W,
+                                long long target, long long tier_lo, long long tier_hi, long long *list,
+                                unsigned long long *count) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool lag = (w < W) && status[w] == 0 && steps[w] < target;
+    const bool lag = (w < W) && status[w] == 0 && steps[w] < target && tier[w] >= tier_lo && tier[w] <= tier_hi;
     const unsigned b = __ballot_sync(0xffffffffu, lag);
     if (b == 0) return;
     const int lane = threadIdx.x & 31;

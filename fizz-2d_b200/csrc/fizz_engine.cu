@@ -153,9 +153,11 @@ struct FizzGroup {
     KernelInfo thread_ki;
     bool thread_ok;
     // hybrid mode
-    KernelInfo ballistic_ki, prover_ki, contact_ki;
+    KernelInfo ballistic_ki, prover_ki, contact_ki, trapped_ki;
     size_t contact_smem, ballistic_smem;
-    long long *sched_list;
+    long long *sched_list, *sched_list2;
+    cudaStream_t side;          // library-owned stream: the trapped instance runs beside the general one
+    cudaEvent_t ev_fork, ev_join;
     unsigned long long *sched_count;  // [0] = count, [1] = cursor
     unsigned char *vbody_dev;
     // optional per-kernel timing (fizz_set_profiling)
@@ -236,7 +238,7 @@ int fizz_layout(const FizzGroupDesc *d, int64_t n_worlds, FizzLayout *out) {
     L.mass = o; o += F * Wp;
     L.verts = o; o += 2 * (int64_t)V * Wp;
     L.energy = o; o += 4 * Wp;
-    L.sched = o; o += Wp + 16;                       // contact-kernel work list + count + cursor (library scratch)
+    L.sched = o; o += 2 * Wp + 16;                   // two work lists + counts/cursors/counters (library scratch)
     L.scene = o;
     o += round_up((int64_t)FV * 6, 16);              // fixed scene constants (library-written)
     o += round_up(((int64_t)V + 7) / 8, 16);         // vertex -> body table
@@ -268,6 +270,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     g->uploaded = false; g->target = 0; g->launches = 0;
     g->mode = FIZZ_MODE_HYBRID; g->chunk = 256;
     g->profile = false; g->ev_used = 0;
+    g->side = nullptr; g->ev_fork = nullptr; g->ev_join = nullptr;
     for (int i = 0; i < 3; i++) { g->prof_ms[i] = 0.0; g->prof_launches[i] = 0; }
     KParams &kp = g->kp;
     double *s = g->slab;
@@ -277,7 +280,8 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     kp.tier = (long long *)(s + L.tier);
     kp.off = s + L.off; kp.thr = s + L.thr; kp.mass = s + L.mass; kp.verts = s + L.verts;
     g->sched_list = (long long *)(s + L.sched);
-    g->sched_count = (unsigned long long *)(s + L.sched + L.stride);
+    g->sched_list2 = (long long *)(s + L.sched + L.stride);
+    g->sched_count = (unsigned long long *)(s + L.sched + 2 * L.stride);
     kp.counters = g->sched_count + 4;
     kp.W = L.n_worlds; kp.Wp = L.stride;
     kp.F = L.n_free; kp.X = L.n_fixed; kp.V = L.n_free_verts;
@@ -340,21 +344,37 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "ballistic kernel setup"); }
     g->contact_smem = contact_smem_bytes(kp.V, kp.FV);
     {
-        static size_t current = 0;
-        e = raise_dynamic_smem(contact_kernel, g->contact_smem, &current);
+        static size_t current_general = 0, current_trapped = 0;
+        e = raise_dynamic_smem(contact_kernel<false>, g->contact_smem, &current_general);
+        if (e == cudaSuccess) e = raise_dynamic_smem(contact_kernel<true>, g->contact_smem, &current_trapped);
     }
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&g->contact_ki.attr, contact_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&g->contact_ki.attr, contact_kernel<false>);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->contact_ki.blocks_per_sm, contact_kernel, CONTACT_BLOCK,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->contact_ki.blocks_per_sm, contact_kernel<false>, CONTACT_BLOCK,
                                                           g->contact_smem);
-    if (e != cudaSuccess || g->contact_ki.blocks_per_sm < 1) { delete g; return cuda_fail(e, "contact kernel setup"); }
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&g->trapped_ki.attr, contact_kernel<true>);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->trapped_ki.blocks_per_sm, contact_kernel<true>, CONTACT_BLOCK,
+                                                          g->contact_smem);
+    if (e != cudaSuccess || g->contact_ki.blocks_per_sm < 1 || g->trapped_ki.blocks_per_sm < 1) {
+        delete g;
+        return cuda_fail(e, "contact kernel setup");
+    }
+    e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "side stream setup"); }
     *out = g;
     return FIZZ_OK;
 }
 
 int fizz_group_destroy(FizzGroup *g) {
-    if (g)
+    if (g) {
         for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
+        if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+        if (g->ev_join) cudaEventDestroy(g->ev_join);
+        if (g->side) cudaStreamDestroy(g->side);
+    }
     delete g;
     return FIZZ_OK;
 }
@@ -470,8 +490,10 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     const dim3 bgrid((unsigned)((W + BALLISTIC_BLOCK - 1) / BALLISTIC_BLOCK));
     const dim3 cgrid((unsigned)((W + 255) / 256));
     // persistent grid: one CTA slot per resident block, but never more warps than worlds
-    const long long kfull = (long long)g->sm_count * g->contact_ki.blocks_per_sm, kneed = (W + CONTACT_WARPS - 1) / CONTACT_WARPS;
-    const dim3 kgrid((unsigned)(kneed < kfull ? kneed : kfull));
+    const long long kneed = (W + CONTACT_WARPS - 1) / CONTACT_WARPS;
+    const long long kfull = (long long)g->sm_count * g->contact_ki.blocks_per_sm;
+    const long long tfull = (long long)g->sm_count * g->trapped_ki.blocks_per_sm;
+    const dim3 kgrid((unsigned)(kneed < kfull ? kneed : kfull)), tgrid((unsigned)(kneed < tfull ? kneed : tfull));
     for (int64_t done = 0; done < n_steps;) {
         const int64_t c = (n_steps - done < g->chunk) ? (n_steps - done) : g->chunk;
         g->target += c;
@@ -489,16 +511,39 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             g->launches += 2;
         }
         cudaEvent_t eb = g->profile ? next_event(g, st) : nullptr;
-        CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
-        classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, W, g->target, g->sched_list, g->sched_count);
-        contact_kernel<<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                      g->sched_count + 1);
+        CU(cudaMemsetAsync(g->sched_count, 0, 4 * sizeof(unsigned long long), st));
+        if (g->mode == FIZZ_MODE_HYBRID) {
+            // latency-tuned: ONE instance (two narrow-phase items per lane, 3 CTAs/SM) steps every lagging world, so the
+            // world with the longest chain of resolve passes never waits for anything
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, g->sched_list,
+                                                   g->sched_count);
+            contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                g->sched_count + 1);
+            g->launches -= 2;
+        } else {
+            // throughput-tuned (hybrid3): two instances run SIDE BY SIDE on disjoint worlds -- the trapped instance (tier
+            // 3 at the start of the chunk) on the library's side stream, the compact high-occupancy general instance
+            // (everything else that lags) on the caller's stream.  Both bring their worlds to the chunk target; the
+            // general instance only FLAGS the worlds it finds trapped, the hand-over happens at the next chunk.
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 3, 3, g->sched_list2,
+                                                   g->sched_count + 2);
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 2, g->sched_list,
+                                                   g->sched_count);
+            CU(cudaEventRecord(g->ev_fork, st));
+            CU(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
+            contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, g->side>>>(kp, g->sched_list2, g->sched_count + 2,
+                                                                                     g->sched_count + 3);
+            CU(cudaEventRecord(g->ev_join, g->side));
+            contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                 g->sched_count + 1);
+            CU(cudaStreamWaitEvent(st, g->ev_join, 0));
+        }
         if (g->profile) {
             g->spans.push_back({FIZZ_KERNEL_BALLISTIC, ea, eb});
             g->spans.push_back({FIZZ_KERNEL_CONTACT, eb, next_event(g, st)});
         }
         CU(cudaGetLastError());
-        g->launches += 4;
+        g->launches += 6;
         done += c;
     }
     return FIZZ_OK;
@@ -617,6 +662,7 @@ int fizz_kernel_info(FizzGroup *g, int32_t which, int32_t *regs, int32_t *smem, 
         case FIZZ_KERNEL_BALLISTIC: ki = &g->ballistic_ki; th = BALLISTIC_BLOCK; sm = 0; break;
         case FIZZ_KERNEL_PROVER: ki = &g->prover_ki; th = BALLISTIC_BLOCK; sm = g->ballistic_smem; break;
         case FIZZ_KERNEL_CONTACT: ki = &g->contact_ki; th = CONTACT_BLOCK; sm = g->contact_smem; break;
+        case FIZZ_KERNEL_TRAPPED: ki = &g->trapped_ki; th = CONTACT_BLOCK; sm = g->contact_smem; break;
         default: return fail(FIZZ_E_ARG, "fizz_kernel_info: unknown kernel id");
     }
     if (regs) *regs = ki->attr.numRegs;

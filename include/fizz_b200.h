@@ -36,15 +36,18 @@ extern "C" {
 #define FIZZ_E_STATE (-3)   /* call sequence error (e.g. step before upload) */
 
 /* execution modes (fizz_set_tuning) */
-#define FIZZ_MODE_HYBRID 1  /* ballistic thread-per-world kernel + warp-per-world contact kernel (default) */
+#define FIZZ_MODE_HYBRID 1  /* ballistic thread-per-world kernel + ONE latency-tuned warp-per-world contact kernel:
+                               best when a few trapped worlds bound the pass (default)                        */
 #define FIZZ_MODE_THREAD 0  /* one thread-per-world kernel with the full semantics                        */
-#define FIZZ_MODE_HYBRID3 2 /* hybrid + a thread-per-world "separation prover" tier between the two: best for busy
-                               scenes (bodies always near fixed geometry) with small chunks (e.g. 32)            */
+#define FIZZ_MODE_HYBRID3 2 /* throughput-tuned: adds a thread-per-world "separation prover" tier and splits the contact
+                               kernel into a compact high-occupancy general instance and a trapped instance that run
+                               side by side: best for busy scenes (use small chunks, e.g. 32)                   */
 /* kernel ids (fizz_kernel_info) */
 #define FIZZ_KERNEL_THREAD 0
 #define FIZZ_KERNEL_BALLISTIC 1
 #define FIZZ_KERNEL_CONTACT 2
 #define FIZZ_KERNEL_PROVER 3
+#define FIZZ_KERNEL_TRAPPED 4
 
 /* per-world status word (slab section `status`) */
 #define FIZZ_ST_RUNNING 0
@@ -98,7 +101,7 @@ typedef struct FizzLayout {
     int64_t steps;      /* [1]   int64 completed update() calls                        */
     int64_t calls;      /* [1]   int64 state-relevant check_collisions() calls, lifetime */
     int64_t vflag;      /* [1]   int64 1 = `verts` holds explicit point.pos (pushed by a resolve pass), 0 = derived */
-    int64_t tier;       /* [1]   int64 scheduling hint: 0 quiescent, 1 broad-phase candidates but no contact, 2 contact phase */
+    int64_t tier;       /* [1]   int64 scheduling hint: 0 quiescent, 1 candidates/no contact, 2 contact phase, 3 trapped */
     int64_t state_words;/* words from `pos` to the end of `tier` */
     /* per-world constants */
     int64_t off;        /* [V*2] |r|cos(phi), |r|sin(phi) per free vertex (physics.py:358-359,632-635) */
@@ -108,7 +111,7 @@ typedef struct FizzLayout {
     int64_t verts;      /* [V*2] point.pos of every free vertex after the last completed launch */
     int64_t energy;     /* [4]   World.energy(): total,kinetic,potential,heat (physics.py:66-74) */
     /* library scratch (never touched by the caller) */
-    int64_t sched;      /* [1]+16 contact-kernel work list, count, cursor */
+    int64_t sched;      /* [2]+16 contact-kernel work lists, counts, cursors, counters */
     int64_t scene;      /* fixed-scene constants + vertex->body table     */
     int64_t total_words;
 } FizzLayout;

@@ -56,7 +56,7 @@ def test_layout_arithmetic():
     assert lay.pos == 0 and lay.vel == 4 * 1024 and lay.heat == 8 * 1024
     assert lay.state_words == (8 + 6) * 1024
     assert lay.off == lay.state_words and lay.thr == lay.off + 14 * 1024
-    assert lay.sched == lay.energy + 4 * 1024 and lay.scene == lay.sched + 1024 + 16
+    assert lay.sched == lay.energy + 4 * 1024 and lay.scene == lay.sched + 2 * 1024 + 16
     assert lay.total_words >= lay.scene + 4 * 6
 
 
