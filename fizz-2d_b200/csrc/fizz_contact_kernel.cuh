@@ -835,11 +835,17 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 }
 
 // Work list for the contact kernel: every running world that has not reached the chunk target.
+// `calls` / rate window: only worlds whose lifetime average of check_collisions() per timestep lies in [rate_lo,
+// rate_hi) are taken (pass calls = nullptr to take all): lets the host append the heaviest worlds first.
 __global__ void classify_kernel(const long long *status, const long long *steps, const long long *tier, long long W,
-                                long long target, long long tier_lo, long long tier_hi, long long *list,
-                                unsigned long long *count) {
+                                long long target, long long tier_lo, long long tier_hi, const long long *calls,
+                                long long rate_lo, long long rate_hi, long long *list, unsigned long long *count) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool lag = (w < W) && status[w] == 0 && steps[w] < target && tier[w] >= tier_lo && tier[w] <= tier_hi;
+    bool lag = (w < W) && status[w] == 0 && steps[w] < target && tier[w] >= tier_lo && tier[w] <= tier_hi;
+    if (lag && calls) {
+        const long long c = calls[w], n = steps[w] > 0 ? steps[w] : 1;
+        lag = c >= rate_lo * n && c < rate_hi * n;
+    }
     const unsigned b = __ballot_sync(0xffffffffu, lag);
     if (b == 0) return;
     const int lane = threadIdx.x & 31;

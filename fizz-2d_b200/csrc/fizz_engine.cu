@@ -14,6 +14,7 @@
 #include "fizz_thread_kernel.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -494,8 +495,14 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     const long long kfull = (long long)g->sm_count * g->contact_ki.blocks_per_sm;
     const long long tfull = (long long)g->sm_count * g->trapped_ki.blocks_per_sm;
     const dim3 kgrid((unsigned)(kneed < kfull ? kneed : kfull)), tgrid((unsigned)(kneed < tfull ? kneed : tfull));
-    for (int64_t done = 0; done < n_steps;) {
-        const int64_t c = (n_steps - done < g->chunk) ? (n_steps - done) : g->chunk;
+    int64_t nchunk = 0;
+    for (int64_t done = 0; done < n_steps; nchunk++) {
+        // chunk length: the tuned value for the first chunks (contact episodes are short and early), then doubling every
+        // second chunk up to 16x: a chunk boundary costs ~0.8 ms of launches and world reloads, and a world the
+        // ballistic kernel hands over late in a long chunk only costs ~0.15 us per quiescent step in the contact kernel
+        static const bool grow = getenv("FIZZ_NO_CHUNK_GROWTH") == nullptr;
+        int64_t len = grow ? (g->chunk << ((nchunk / 2 < 4) ? nchunk / 2 : 4)) : g->chunk;
+        const int64_t c = (n_steps - done < len) ? (n_steps - done) : len;
         g->target += c;
         kp.target_steps = g->target;
         cudaEvent_t ea = g->profile ? next_event(g, st) : nullptr;
@@ -515,8 +522,10 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         if (g->mode == FIZZ_MODE_HYBRID) {
             // latency-tuned: ONE instance (two narrow-phase items per lane, 3 CTAs/SM) steps every lagging world, so the
             // world with the longest chain of resolve passes never waits for anything
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, g->sched_list,
-                                                   g->sched_count);
+            // (work list in world order: measured -- grouping the trapped worlds at the head of the list, or sorting them
+            //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, nullptr, 0, 1,
+                                                   g->sched_list, g->sched_count);
             contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
                                                                                 g->sched_count + 1);
             g->launches -= 2;
@@ -525,9 +534,9 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             // 3 at the start of the chunk) on the library's side stream, the compact high-occupancy general instance
             // (everything else that lags) on the caller's stream.  Both bring their worlds to the chunk target; the
             // general instance only FLAGS the worlds it finds trapped, the hand-over happens at the next chunk.
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 3, 3, g->sched_list2,
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 3, 3, nullptr, 0, 1, g->sched_list2,
                                                    g->sched_count + 2);
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 2, g->sched_list,
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 2, nullptr, 0, 1, g->sched_list,
                                                    g->sched_count);
             CU(cudaEventRecord(g->ev_fork, st));
             CU(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
