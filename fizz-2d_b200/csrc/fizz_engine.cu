@@ -526,8 +526,15 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
             classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, nullptr, 0, 1,
                                                    g->sched_list, g->sched_count);
-            contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                g->sched_count + 1);
+            // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
+            // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
+            static const bool first_general = getenv("FIZZ_NO_FIRST_GENERAL") == nullptr;
+            if (g->target == c && first_general)
+                contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                     g->sched_count + 1);
+            else
+                contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                    g->sched_count + 1);
             g->launches -= 2;
         } else {
             // throughput-tuned (hybrid3): two instances run SIDE BY SIDE on disjoint worlds -- the trapped instance (tier
