@@ -433,11 +433,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 
     const long long Wp = kp.Wp;
     const unsigned long long count = *count_ptr;
-#ifdef FIZZ_EXPERIMENT_NO_FAST
-    const bool speculate = false;
-#else
     const bool speculate = (kp.trace == nullptr);  // the contact trace needs every trial's tuples: sequential then
-#endif
 
     for (;;) {
         unsigned long long idx = 0;

@@ -14,7 +14,6 @@
 #include "fizz_thread_kernel.cuh"
 
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -500,8 +499,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         // chunk length: the tuned value for the first chunks (contact episodes are short and early), then doubling every
         // second chunk up to 16x: a chunk boundary costs ~0.8 ms of launches and world reloads, and a world the
         // ballistic kernel hands over late in a long chunk only costs ~0.15 us per quiescent step in the contact kernel
-        static const bool grow = getenv("FIZZ_NO_CHUNK_GROWTH") == nullptr;
-        int64_t len = grow ? (g->chunk << ((nchunk / 2 < 4) ? nchunk / 2 : 4)) : g->chunk;
+        const int64_t len = g->chunk << ((nchunk / 2 < 4) ? nchunk / 2 : 4);
         const int64_t c = (n_steps - done < len) ? (n_steps - done) : len;
         g->target += c;
         kp.target_steps = g->target;
@@ -528,8 +526,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                                                    g->sched_list, g->sched_count);
             // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
             // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
-            static const bool first_general = getenv("FIZZ_NO_FIRST_GENERAL") == nullptr;
-            if (g->target == c && first_general)
+            if (g->target == c)
                 contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
                                                                                      g->sched_count + 1);
             else

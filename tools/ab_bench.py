@@ -1,4 +1,6 @@
-"""Same-box A/B: total ms of one 10k-step pass of the benchmark batch, alternating env settings (argv pairs K=V)."""
+"""Same-box A/B harness: total ms of one 10k-step pass of the benchmark batch, alternating environment settings
+(argv entries K=V or `base`).  Box-to-box and run-to-run noise is +-2 %: only trust comparisons made inside ONE gpurun call.
+(The engine currently reads no environment variables; add a getenv toggle around the code under test.)"""
 import os, subprocess, sys
 variants = sys.argv[1:]
 code = '''
