@@ -331,6 +331,10 @@ def run_gpu(args):
                 if sec > 0:
                     rk[name] = {"bound": "fp64", "achieved": ops / sec / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
                                 "frac": ops / sec / 1e12 / peak_tflops, "ms_per_pass": prof[name][0] / args.steps}
+            if "ballistic" in rk and W == 65536 and args.mode == "hybrid":
+                # per launch; from profiles/r01_ballistic_raw.csv (ncu --set full, dram__bytes_read.sum + write.sum)
+                rk["ballistic"]["traffic"] = 19.94e6
+                rk["ballistic"]["algorithmic_bytes_per_launch"] = 8 * W * (5 * F_)   # pos, vel, thr rows read once
             line["roofline_by_kernel"] = rk
             line["roofline"] = dict(rk[dom], traffic=None, kernel=dom + "_kernel", ops_per_world_step=ops_per_ws,
                                     quiescent_ops_per_world_step=q_ops,
