@@ -44,6 +44,7 @@ __device__ __noinline__ bool prove_separated(const double *sfix, const double *s
                                                 int ii, int jj, double Mi, double Mj) {
     const int n1 = stab[ii], v1 = stab[32 + ii];
     const int n2 = stab[jj], v2 = stab[32 + jj];
+    FIZZ_ASSERT(ii >= 0 && ii < F && jj > ii && jj < TAB && n1 >= 3 && n2 >= 3);
     const double c1x = snp[(2 * ii) * BALLISTIC_BLOCK + tid], c1y = snp[(2 * ii + 1) * BALLISTIC_BLOCK + tid];
 #define FZ_V1X(v) (offp[(long long)(2 * (v1 + (v))) * ostride + obase] + c1x)
 #define FZ_V1Y(v) (offp[(long long)(2 * (v1 + (v)) + 1) * ostride + obase] + c1y)
@@ -132,6 +133,7 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
     const long long t = (long long)blockIdx.x * BALLISTIC_BLOCK + tid;
     if (t >= (long long)*count_ptr) return;
     const long long w = list[t];
+    FIZZ_ASSERT(w >= 0 && w < kp.W);
     const long long step0 = kp.steps[w];
     const long long Wp = kp.Wp;
     double px[F], py[F], vx[F], vy[F], thr[F];

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
 
 namespace fizz {
 
@@ -38,6 +39,20 @@ struct KParams {
     double vib_thr;            // T(vib_tol): norm(nv) > VIBRATE_TOL  <=>  fma(nvy,nvy,nvx*nvx) > vib_thr  (:180)
     int max_calls;
 };
+
+// Debug builds (-DFIZZ_DEBUG): index checks that trap instead of corrupting memory (compute-sanitizer is closed on
+// the development pool).  Release builds compile them out.
+#ifdef FIZZ_DEBUG
+#define FIZZ_ASSERT(cond)                                                                  \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            printf("FIZZ_ASSERT failed: %s  (%s:%d)\n", #cond, __FILE__, __LINE__);        \
+            __trap();                                                                      \
+        }                                                                                  \
+    } while (0)
+#else
+#define FIZZ_ASSERT(cond) ((void)0)
+#endif
 
 __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
 

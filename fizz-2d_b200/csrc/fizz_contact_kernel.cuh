@@ -114,6 +114,7 @@ __device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, pairmeta_t
     const double *vert = s.vert;
     double lo2 = 0.0, hi2 = 0.0;
     bool own2 = false;
+    FIZZ_ASSERT(k >= 0 && k < n1 + n2 && n1 >= 3 && n2 >= 3 && PM_II(m) < F);
     if (k < n1) {
         const int k2 = (k + 1 == n1) ? 0 : k + 1;
         edge_normal<true>(s, v1 + k, vert[2 * (v1 + k)], vert[2 * (v1 + k) + 1], vert[2 * (v1 + k2)],
@@ -244,6 +245,7 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     const unsigned FULL = 0xffffffffu;
     const int n1 = N1 ? N1 : kp.nv[b];
     const int v1 = kp.vs[b];
+    FIZZ_ASSERT(b >= 0 && b < F && n1 <= NM && (!N1 || kp.nv[b] == N1));
     double cpx = s.px[b], cpy = s.py[b], cvx = s.vx[b], cvy = s.vy[b];
     const double m1 = s.mass[b], thr_b = s.thr[b];
     double vtx[NM], vty[NM];
@@ -441,6 +443,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= count) break;
         const long long w = list[idx];
+        FIZZ_ASSERT(w >= 0 && w < kp.W);
 
         // ---- load the world into the warp's shared-memory slice ------------------------------------------------
         if (lane < F) {
@@ -506,6 +509,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         surv = !(d2 > s.thr[i] && d2 > ot);
                     }
                     const unsigned b = __ballot_sync(FULL, surv);
+                    FIZZ_ASSERT(ns + __popc(b) <= SP_CAP);
                     if (surv) s.sp[ns + __popc(b & lt_mask)] = m;
                     ns += __popc(b);
                 }
