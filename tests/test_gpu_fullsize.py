@@ -1,0 +1,83 @@
+"""GPU: BASELINE.json's full sizes, checked through size-independent properties (the oracle would need hours):
+energy bookkeeping, the unperturbed anchor world inside the batch, random samples against the oracle, and mode
+independence."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fizz2d_b200 as fz
+from conftest import GOLDEN, scene_file
+from helpers import bits, oracle_from_spec, orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config3_full_size_properties():
+    """RAMPWORLD x 65536 worlds x 1000 steps (seed 20260003): ELASTICITY is 1, so no heat is ever booked and the
+    kinetic energy of every uncapped world is conserved to rounding; world 0 is the SURVEY 8c anchor row; a random
+    sample of 96 worlds equals the oracle bit for bit."""
+    with open(os.path.join(GOLDEN, "anchors.json")) as f:
+        anchor = json.load(f)["RAMPWORLD_2TRIANGLES_5SQUARES"]
+    bw = fz.BatchedWorld.from_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=65536, perturb=True, seed=20260003)
+    e0 = bw.energy()
+    bw.step(1000)
+    e1, st, sd, com, calls = bw.energy(), bw.status(), bw.steps_done(), bw.com(), bw.calls()
+    ok = st == 0
+    assert 40000 < ok.sum() < 60000 and (sd[ok] == 1000).all() and (sd[~ok] < 1000).all()
+    assert (e1[ok, 3] == 0).all() and (e1[ok, 2] == 0).all()
+    assert (np.abs(e1[ok, 0] - e0[ok, 0]) / e0[ok, 0]).max() < 1e-9
+    assert np.array_equal(bits(e1[0]), bits(anchor["final_energy"]))
+    assert np.array_equal(bits(com[0]), bits(anchor["final_com"]))
+    assert calls[0] == anchor["calls_relevant"]
+    rng = np.random.default_rng(5)
+    sample = rng.choice(65536, 96, replace=False)
+    spec = bw.groups[0].spec
+    worlds = [oracle_from_spec(spec, int(w)) for w in sample]
+    orc.run_batch(worlds, 1000, os.cpu_count() or 1)
+    for w, ow in zip(sample, worlds):
+        assert ow.steps_done() == sd[w] and ow.status() == st[w], w
+        assert np.array_equal(bits(ow.com()), bits(com[w])), w
+        assert ow.total_calls() == calls[w], w
+
+
+def test_config4_full_size_properties():
+    """262144 mixed worlds (2CHAMBERS / STACKEDCHAMBERS, seed 20260004) x 300 steps in the throughput mode:
+    a random sample equals the oracle; energy is conserved or dissipated, never created."""
+    paths = [scene_file("2CHAMBERS_3BALLS"), scene_file("STACKEDCHAMBERS_1SQUARE")]
+    bw = fz.BatchedWorld.from_mixed(paths, 262144, seed=20260004, max_calls=512)
+    bw.set_tuning("hybrid3", 32)
+    e0 = bw.energy()
+    bw.step(300)
+    e1, st, sd, heat, calls = bw.energy(), bw.status(), bw.steps_done(), bw.heat(), bw.calls()
+    ok = st == 0
+    assert ok.mean() > 0.99 and (sd[ok] == 300).all()
+    moving = ok & (e0[:, 0] > 0)
+    assert (np.abs(e1[moving, 0] - e0[moving, 0]) / e0[moving, 0]).max() < 1e-9      # K + H is conserved
+    assert (heat >= 0).all()
+    com = bw.com()
+    rng = np.random.default_rng(9)
+    for w in rng.choice(262144, 64, replace=False):
+        gi, k = bw.locate(int(w))
+        ow = oracle_from_spec(bw.groups[gi].spec, k)
+        ow.run(300)
+        assert ow.steps_done() == sd[w] and ow.status() == st[w], w
+        assert np.array_equal(bits(ow.com()), bits(com[gi][k])), w
+        assert bits(ow.heat()) == bits(heat[w]) and ow.total_calls() == calls[w], w
+
+
+def test_compat_world_api():
+    """The drop-in World: update(), str(), energy(), heat, state behave like physics.World for the viewed world."""
+    from fizz2d_b200 import compat
+    from conftest import golden
+    g = golden("BOX_1SQUARE")
+    w = compat.read_input(scene_file("BOX_1SQUARE"))
+    assert (w.width, w.height) == (500, 300) and w.state == 0
+    for t in range(12):
+        assert np.array_equal(bits(w.energy()), bits(g["energy_before"][t]))
+        w.update()
+    assert abs(w.state - 12 * 0.05) < 1e-12
+    assert bits(w.heat) == bits(g["heat"][11])
+    text = str(w)
+    assert text.startswith("500,300\npolygon\nsides,4\npoint,") and text.count("polygon") == 5
