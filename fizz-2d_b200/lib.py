@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfizz_b200.so")
+LIB_PATH = os.environ.get("FIZZ_B200_LIB") or os.path.join(HERE, "libfizz_b200.so")  # override: A/B of builds
 
 MAX_FREE, MAX_FIXED, MAX_POLY_VERTS, MAX_FIXED_VERTS, MAX_HITS = 8, 16, 16, 96, 32
 ST_RUNNING, ST_CAPPED, ST_NONFINITE, ST_HIT_OVERFLOW = 0, 1, 2, 3
