@@ -227,6 +227,15 @@ def run_gpu(args):
         flush.fill_(1)
         pass_resident()
     barrier()
+    if world_size > 1:
+        # the gather puts world w of the global batch at column w on every rank: this rank's columns are its shard
+        full = gather_results()
+        fz.lib.check(fz.lib.load().fizz_energy(g.handle, torch.cuda.current_stream().cuda_stream))
+        mine = fd.pack_results(g.section("energy", 4), g.section("heat", 1)[0], g.section("status", 1, torch.int64)[0])
+        idx = torch.from_numpy(fd.shard_indices(W * world_size, rank, world_size)).to(dev)
+        assert full.shape == (fd.RESULT_ROWS, W * world_size)
+        assert torch.equal(full[:, idx].view(torch.int64), mine.view(torch.int64)), "NCCL gather misplaced this rank's worlds"
+        barrier()
 
     # ---- timed: resident --------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
