@@ -345,7 +345,10 @@ def run_gpu(args):
                 rk["ballistic"]["traffic"] = 19.94e6
                 rk["ballistic"]["algorithmic_bytes_per_launch"] = 8 * W * (5 * F_)   # pos, vel, thr rows read once
             line["roofline_by_kernel"] = rk
-            line["roofline"] = dict(rk[dom], traffic=None, kernel=dom + "_kernel", ops_per_world_step=ops_per_ws,
+            # DRAM bytes of one launch of the dominant kernel from profiles/r01_final_kernels_raw.csv (ncu --set full,
+            # steady-state contact launch): 49.5 MB read + 0.3 MB written -- the state slab once; irrelevant next to HBM
+            dom_traffic = 49.8e6 if (dom == "contact" and W == 65536) else None
+            line["roofline"] = dict(rk[dom], traffic=dom_traffic, kernel=dom + "_kernel", ops_per_world_step=ops_per_ws,
                                     quiescent_ops_per_world_step=q_ops,
                                     peak_source="fizz_fp64_peak(): DFMA microbenchmark on this GPU at bench start "
                                                 "(MEASURED_PEAKS.json has no FP64 figure)",
