@@ -248,12 +248,6 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     FIZZ_ASSERT(b >= 0 && b < F && n1 <= NM && (!N1 || kp.nv[b] == N1));
     double cpx = s.px[b], cpy = s.py[b], cvx = s.vx[b], cvy = s.vy[b];
     const double m1 = s.mass[b], thr_b = s.thr[b];
-    double vtx[NM], vty[NM];
-#pragma unroll
-    for (int v = 0; v < NM; v++) {
-        vtx[v] = (v < n1) ? s.vert[2 * (v1 + v)] : 0.0;
-        vty[v] = (v < n1) ? s.vert[2 * (v1 + v) + 1] : 0.0;
-    }
     // this lane's broad-phase partner: body `lane` of objs+fixed_objs.  (a-b)^2 == (b-a)^2 exactly, so the order of
     // the subtraction at :277 does not matter.
     const bool partner = (lane < F + X) && (lane != b);
@@ -284,22 +278,31 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     const bool active = (jj >= 0) && (k < n1 + n2);
     const bool freeaxis = active && (k < n1);
     const unsigned live_bytes_all = (ncand >= 4) ? 0xffffffffu : ((1u << (8 * ncand)) - 1u);
-    // axis registers of this lane: unit normal, the partner's projection bounds on it, and -- for an edge of b -- the
-    // edge end points plus the exact edge vector the normal was computed from (memo key; NaN = not computed yet).
-    double anx = 0.0, any_ = 0.0, alo2 = 0.0, ahi2 = 0.0;
-    double ex0 = 0.0, ey0 = 0.0, ex1 = 0.0, ey1 = 0.0, keyx = 0.0, keyy = 0.0;
-    if (freeaxis) {
-        const int k2 = (k + 1 == n1) ? 0 : k + 1;
-        ex0 = s.vert[2 * (v1 + k)]; ey0 = s.vert[2 * (v1 + k) + 1];
-        ex1 = s.vert[2 * (v1 + k2)]; ey1 = s.vert[2 * (v1 + k2) + 1];
-        keyx = NAN; keyy = NAN;
-    } else if (active) {
+    // b's vertices, all of them in every lane, ROTATED so that a lane that owns edge k of b finds the edge's end points
+    // in registers 0 and 1 (min/max over the same set of projections: only the sign of a zero could depend on order).
+    const int rot = freeaxis ? k : 0;
+    double vtx[NM], vty[NM];
+#pragma unroll
+    for (int v = 0; v < NM; v++) {
+        int src = rot + v;
+        if (src >= n1) src -= n1;
+        vtx[v] = (v < n1) ? s.vert[2 * (v1 + src)] : 0.0;
+        vty[v] = (v < n1) ? s.vert[2 * (v1 + src) + 1] : 0.0;
+    }
+    // axis registers of this lane: unit normal, the partner's projection bounds on it and -- for an edge of b -- the
+    // exact edge vector the normal was computed from (memo key; NaN = not computed yet).
+    double anx = 0.0, any_ = 0.0, alo2 = 0.0, ahi2 = 0.0, keyx = NAN, keyy = NAN;  // (keys only used by edge lanes)
+    if (active && !freeaxis) {
         const double *g = s.sfix + (v2 + (k - n1)) * 6;
         anx = g[2]; any_ = g[3]; alo2 = g[4]; ahi2 = g[5];
     }
+    int passes = 0;
+    const int budget = kp.max_calls - ncalls;  // watchdog: the general path raises FIZZ_ST_CAPPED
+    // (a "travel budget" that skips the broad phase while b cannot have reached a partner's threshold was measured and
+    //  dropped: trapped bodies jump 20-100 px per pass, the budget is exhausted almost every pass)
 
     for (;;) {
-        if (ncalls >= kp.max_calls) break;  // watchdog: the general path raises FIZZ_ST_CAPPED
+        if (passes >= budget) break;
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
         {
             const double dx = cpx - ox, dy = cpy - oy;
@@ -308,10 +311,9 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         }
         // ---- narrow phase: one (partner, axis) item per lane ----------------------------------------------------
         {
-            // edge vector of b's edge (zero for a partner-axis lane: its key stays (0,0))
-            const double ax = ey1 - ey0, ay = ex0 - ex1;
-            const bool miss = (__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
-                              (__double_as_longlong(ay) != __double_as_longlong(keyy));
+            const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];  // edge k of b: (p2.y - p1.y, p1.x - p2.x)
+            const bool miss = freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
+                                           (__double_as_longlong(ay) != __double_as_longlong(keyy)));
             if (miss) {  // rare (<2%): new edge vector -> new unit normal (:790) and new partner bounds (:806-811)
                 const double nrm = sqrt(fma(ay, ay, ax * ax));
                 anx = ax / nrm; any_ = ay / nrm; keyx = ax; keyy = ay;
@@ -362,14 +364,12 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         const int wl = __ffs(winb) - 1;  // lowest axis index among equal minima
         const double mag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
         const double ux = __shfl_sync(FULL, anx, wl) * -1.0, uy = __shfl_sync(FULL, any_, wl) * -1.0;  // :838-839
-        ncalls++;
-        ncalls_total++;
+        passes++;
         // ---- resolution, free body vs fixed body (:171-198) -----------------------------------------------------
         const double sc = mag + kp.eps;                                          // :158
         const double nvx = ux * sc, nvy = uy * sc;
 #pragma unroll
         for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }           // :174
-        ex0 += nvx; ey0 += nvy; ex1 += nvx; ey1 += nvy;
         if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }   // :180-181
         const double vdotN = dot2(cvx, cvy, ux, uy);                             // :183
         const double cc = kp.ope * vdotN;                                        // :188
@@ -377,11 +377,11 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         cvy -= cc * uy;
         heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
     }
+    ncalls += passes;
+    ncalls_total += passes;
     // ---- write the state back for the general path ----------------------------------------------------------------
     __syncwarp();
-#pragma unroll
-    for (int v = 0; v < NM; v++)
-        if (lane == v && v < n1) { s.vert[2 * (v1 + v)] = vtx[v]; s.vert[2 * (v1 + v) + 1] = vty[v]; }
+    if (lane < n1) { s.vert[2 * (v1 + lane)] = vtx[0]; s.vert[2 * (v1 + lane) + 1] = vty[0]; }  // slot 0, k = lane
     if (freeaxis && slot == 0 && keyx == keyx) {
         s.max_[v1 + k] = keyx; s.may_[v1 + k] = keyy; s.mnx[v1 + k] = anx; s.mny[v1 + k] = any_;
     }
