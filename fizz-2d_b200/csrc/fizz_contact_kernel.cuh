@@ -277,7 +277,8 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     if (jj >= 0) { n2 = kp.nv[jj]; v2 = kp.vs[jj]; }
     const bool active = (jj >= 0) && (k < n1 + n2);
     const bool freeaxis = active && (k < n1);
-    const unsigned live_bytes_all = (ncand >= 4) ? 0xffffffffu : ((1u << (8 * ncand)) - 1u);
+    const bool active_slot = (jj >= 0);
+    const unsigned slot_bits = 0xffu << (8 * slot);
     // b's vertices, all of them in every lane, ROTATED so that a lane that owns edge k of b finds the edge's end points
     // in registers 0 and 1 (min/max over the same set of projections: only the sign of a zero could depend on order).
     const int rot = freeaxis ? k : 0;
@@ -300,21 +301,87 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     const int budget = kp.max_calls - ncalls;  // watchdog: the general path raises FIZZ_ST_CAPPED
     // (a "travel budget" that skips the broad phase while b cannot have reached a partner's threshold was measured and
     //  dropped: trapped bodies jump 20-100 px per pass, the budget is exhausted almost every pass)
+    //
+    // Shape of the loop.  One warp runs this chain alone, so dependent-issue LATENCY sets its speed, and control flow is
+    // the most expensive instruction class there is (tools/micro/latency.cu on B200: a taken branch ~22 cycles, a
+    // BSSY/BRA/BSYNC guarded block ~47, against 8 for a DFMA and 18 for a redux).  The hot loop therefore has exactly
+    // one branch, its back edge: check() evaluates a whole check_collisions() without side effects and says whether
+    // its result is the plain case (same candidates, one colliding partner, memoised normals valid, finite overlap,
+    // watchdog not due); the loop body applies that result and checks again.  Everything else -- a stale edge-normal
+    // memo (<2% of the passes) or the hand-over to the general path -- happens outside the hot loop.
+    const bool surv0 = surv;
+    const double tmax = (thr_b > ot) ? thr_b : ot;  // d2 > thr_b && d2 > ot  <=>  d2 > max(thr_b, ot)  (:277, finite radii)
+    bool miss = false;
+    double wnx = 0.0, wny = 0.0, mag = 0.0;
+
+    auto check = [&]() -> bool {
+        // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
+        const double dx = cpx - ox, dy = cpy - oy;
+        const double d2 = fma(dy, dy, dx * dx);
+        surv = partner && !(d2 > tmax);
+        // ---- memo check: edge k of b is (p2.y - p1.y, p1.x - p2.x) (:788-789) ----------------------------------------
+        const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
+        miss = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
+                            ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
+        const bool bad = __any_sync(FULL, (surv != surv0) | miss);
+        // ---- narrow phase: one (partner, axis) item per lane --------------------------------------------------------
+        double lo1, hi1;
+        if constexpr (N1 == 4) {                                                 // :795-804 as a two-level tree
+            const double c0 = dot2(anx, any_, vtx[0], vty[0]), c1 = dot2(anx, any_, vtx[1], vty[1]);
+            const double c2 = dot2(anx, any_, vtx[2], vty[2]), c3 = dot2(anx, any_, vtx[3], vty[3]);
+            const double la = (c1 < c0) ? c1 : c0, ha = (c1 > c0) ? c1 : c0;
+            const double lb = (c3 < c2) ? c3 : c2, hb = (c3 > c2) ? c3 : c2;
+            lo1 = (lb < la) ? lb : la;
+            hi1 = (hb > ha) ? hb : ha;
+        } else {
+            lo1 = hi1 = dot2(anx, any_, vtx[0], vty[0]);                         // :795
+#pragma unroll
+            for (int v = 1; v < NM; v++) {                                       // :799-804
+                if (N1 || v < n1) {
+                    const double c = dot2(anx, any_, vtx[v], vty[v]);
+                    if (c < lo1) lo1 = c;
+                    if (c > hi1) hi1 = c;
+                }
+            }
+        }
+        double lo2 = alo2, hi2 = ahi2;
+        if (lo1 > lo2) {                                                         // :815-817
+            double t = lo1; lo1 = lo2; lo2 = t;
+            t = hi1; hi1 = hi2; hi2 = t;
+        }
+        // lanes of slots without a candidate count as separated: a zero byte of sepbits <=> a colliding partner
+        const bool sep = !active_slot || (active && (hi1 < lo2));                // :820
+        const double cur = hi1 - lo2;                                            // :824
+        const unsigned sepbits = __ballot_sync(FULL, sep);
+        // first strict minimum in axis order (:827-830) over the 8 lanes of the live slot: three 32-bit redux.sync.min
+        // (high word, low word, lane).  Overlaps of a non-separated pair are >= +0.0 -- or the -0.0 of (-0.0) - (+0.0),
+        // hence the sign mask: `cur < overlap` is false between the two zeros and the push uses mag = fabs(overlap) --
+        // so their bit patterns order like unsigned integers; +inf and NaN order above every finite overlap and never
+        // win against one (`cur < overlap` with overlap = inf is false for them): if the minimum is one of them the
+        // general path takes over.
+        const bool mine = active && ((sepbits & slot_bits) == 0u);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(cur);
+        const unsigned hiw = (unsigned)(bits >> 32) & 0x7fffffffu, low = (unsigned)bits;
+        const unsigned mhi = __reduce_min_sync(FULL, mine ? hiw : 0xffffffffu);
+        const bool m1_ = mine && hiw == mhi;
+        const unsigned mlo = __reduce_min_sync(FULL, m1_ ? low : 0xffffffffu);
+        const bool m2_ = m1_ && low == mlo;
+        const unsigned wl = __reduce_min_sync(FULL, m2_ ? (unsigned)lane : 32u);  // lowest axis index among equal minima
+        // exactly one candidate slot without a separating axis: bit 7 of each NON-zero byte, then "one bit left"
+        const unsigned nzb = (((sepbits & 0x7f7f7f7fu) + 0x7f7f7f7fu) | sepbits) & 0x80808080u;
+        const unsigned zb = nzb ^ 0x80808080u;  // (no zero byte at all -> no lane is `mine` -> mhi = 0xffffffff)
+        mag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+        wnx = __shfl_sync(FULL, anx, wl);                                        // the winning axis (:828-830)
+        wny = __shfl_sync(FULL, any_, wl);
+        return !bad && (zb & (zb - 1u)) == 0u && mhi < 0x7ff00000u && passes < budget;
+    };
 
     for (;;) {
-        if (passes >= budget) break;
-        // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
+        // ---- refresh the memo of the lanes whose edge vector changed: unit normal (:790), partner bounds (:806-811) -
         {
-            const double dx = cpx - ox, dy = cpy - oy;
-            const double d2 = fma(dy, dy, dx * dx);
-            surv = partner && !(d2 > thr_b && d2 > ot);
-        }
-        // ---- narrow phase: one (partner, axis) item per lane ----------------------------------------------------
-        {
-            const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];  // edge k of b: (p2.y - p1.y, p1.x - p2.x)
-            const bool miss = freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
-                                           (__double_as_longlong(ay) != __double_as_longlong(keyy)));
-            if (miss) {  // rare (<2%): new edge vector -> new unit normal (:790) and new partner bounds (:806-811)
+            const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
+            if (freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
+                             (__double_as_longlong(ay) != __double_as_longlong(keyy)))) {
                 const double nrm = sqrt(fma(ay, ay, ax * ax));
                 anx = ax / nrm; any_ = ay / nrm; keyx = ax; keyy = ay;
                 const double *g = s.sfix + v2 * 6;
@@ -325,57 +392,26 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
                     if (c > ahi2) ahi2 = c;
                 }
             }
+            __syncwarp();
         }
-        double lo1, hi1;
-        lo1 = hi1 = dot2(anx, any_, vtx[0], vty[0]);                             // :795
+        bool ok = check();
+        while (ok) {
+            // ---- resolution, free body vs fixed body (:171-198) -------------------------------------------------
+            passes++;
+            const double ux = wnx * -1.0, uy = wny * -1.0;                           // :838-839
+            const double sc = mag + kp.eps;                                          // :158
+            const double nvx = ux * sc, nvy = uy * sc;
 #pragma unroll
-        for (int v = 1; v < NM; v++) {                                           // :799-804
-            if (N1 || v < n1) {
-                const double c = dot2(anx, any_, vtx[v], vty[v]);
-                if (c < lo1) lo1 = c;
-                if (c > hi1) hi1 = c;
-            }
+            for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }           // :174
+            if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }   // :180-181
+            const double vdotN = dot2(cvx, cvy, ux, uy);                             // :183
+            const double cc = kp.ope * vdotN;                                        // :188
+            cvx -= cc * ux;
+            cvy -= cc * uy;
+            heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
+            ok = check();
         }
-        double lo2 = alo2, hi2 = ahi2;
-        if (lo1 > lo2) {                                                         // :815-817
-            double t = lo1; lo1 = lo2; lo2 = t;
-            t = hi1; hi1 = hi2; hi2 = t;
-        }
-        const bool sep = active && (hi1 < lo2);                                  // :820
-        const double cur = hi1 - lo2;                                            // :824
-        const unsigned survb = __ballot_sync(FULL, surv);
-        const unsigned sepbits = __ballot_sync(FULL, sep);
-        // slots (bytes of sepbits) whose pair has no separating axis; exactly one of the candidate slots may be live
-        const unsigned livebytes = __vcmpeq4(sepbits, 0u) & live_bytes_all;   // 0xff per live slot
-        const bool my_live = (livebytes >> (8 * slot)) & 1u;
-        // first strict minimum in axis order (:827-830) over the 8 lanes of the live slot.  Overlaps of a non-separated
-        // pair are >= +0.0, so their bit patterns order like unsigned integers: two 32-bit redux.sync.min.
-        // (-0.0 orders like +0.0: `cur < overlap` is false between them and the push n*(mag+EPSILON) is the same)
-        const bool mine = active && my_live && (cur < INFINITY);
-        const unsigned long long bits = (cur == 0.0) ? 0ull : (unsigned long long)__double_as_longlong(cur);
-        const unsigned khi = mine ? (unsigned)(bits >> 32) : 0xffffffffu;
-        const unsigned mhi = __reduce_min_sync(FULL, khi);
-        const unsigned klo = (mine && khi == mhi) ? (unsigned)bits : 0xffffffffu;
-        const unsigned mlo = __reduce_min_sync(FULL, klo);
-        const unsigned winb = __ballot_sync(FULL, mine && khi == mhi && (unsigned)bits == mlo);
-        // one exit test per pass: other candidate set | zero or several colliding partners (the resolve loop ends,
-        // or the general path takes over) | no comparable overlap (NaN axes)
-        if (survb != mask0 || __popc(livebytes) != 8 || mhi == 0xffffffffu || winb == 0) break;
-        const int wl = __ffs(winb) - 1;  // lowest axis index among equal minima
-        const double mag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-        const double ux = __shfl_sync(FULL, anx, wl) * -1.0, uy = __shfl_sync(FULL, any_, wl) * -1.0;  // :838-839
-        passes++;
-        // ---- resolution, free body vs fixed body (:171-198) -----------------------------------------------------
-        const double sc = mag + kp.eps;                                          // :158
-        const double nvx = ux * sc, nvy = uy * sc;
-#pragma unroll
-        for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }           // :174
-        if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }   // :180-181
-        const double vdotN = dot2(cvx, cvy, ux, uy);                             // :183
-        const double cc = kp.ope * vdotN;                                        // :188
-        cvx -= cc * ux;
-        cvy -= cc * uy;
-        heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
+        if (!__any_sync(FULL, miss)) break;  // (with a stale memo the check above decided nothing: refresh, check again)
     }
     ncalls += passes;
     ncalls_total += passes;
