@@ -19,6 +19,8 @@
 //     lane 0.
 #pragma once
 
+#include <type_traits>
+
 #include "fizz_common.cuh"
 
 namespace fizz {
@@ -314,16 +316,12 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     bool miss = false;
     double wnx = 0.0, wny = 0.0, mag = 0.0;
 
-    auto check = [&]() -> bool {
-        // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
-        const double dx = cpx - ox, dy = cpy - oy;
-        const double d2 = fma(dy, dy, dx * dx);
-        surv = partner && !(d2 > tmax);
-        // ---- memo check: edge k of b is (p2.y - p1.y, p1.x - p2.x) (:788-789) ----------------------------------------
-        const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
-        miss = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
-                            ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
-        const bool bad = __any_sync(FULL, (surv != surv0) | miss);
+    // (the latency of one warp is also why the statements below are ordered the way they are: the chain
+    //  push -> vertices -> projections -> ballot -> three redux -> shuffle comes first, and the rest of a pass --
+    //  velocity, heat, centre of mass, broad phase, memo check -- is issued while the warp-wide reductions are in flight)
+    double pux = 0.0, puy = 0.0, pnvx = 0.0, pnvy = 0.0;  // previous pass: normal and push, for the deferred part
+
+    auto check = [&](auto first) -> bool {
         // ---- narrow phase: one (partner, axis) item per lane --------------------------------------------------------
         double lo1, hi1;
         if constexpr (N1 == 4) {                                                 // :795-804 as a two-level tree
@@ -363,10 +361,28 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         const unsigned long long bits = (unsigned long long)__double_as_longlong(cur);
         const unsigned hiw = (unsigned)(bits >> 32) & 0x7fffffffu, low = (unsigned)bits;
         const unsigned mhi = __reduce_min_sync(FULL, mine ? hiw : 0xffffffffu);
+        if constexpr (!decltype(first)::value) {
+            // ---- rest of the previous resolution, free body vs fixed body (:180-198) ------------------------------
+            if (fma(pnvy, pnvy, pnvx * pnvx) > kp.vib_thr) { cpx += pnvx; cpy += pnvy; }   // :180-181
+            const double vdotN = dot2(cvx, cvy, pux, puy);                           // :183
+            const double cc = kp.ope * vdotN;                                        // :188
+            cvx -= cc * pux;
+            cvy -= cc * puy;
+            heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
+        }
         const bool m1_ = mine && hiw == mhi;
         const unsigned mlo = __reduce_min_sync(FULL, m1_ ? low : 0xffffffffu);
+        // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
+        const double dx = cpx - ox, dy = cpy - oy;
+        const double d2 = fma(dy, dy, dx * dx);
+        surv = partner && !(d2 > tmax);
+        // ---- memo check: edge k of b is (p2.y - p1.y, p1.x - p2.x) (:788-789) ----------------------------------------
+        const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
+        miss = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
+                            ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
         const bool m2_ = m1_ && low == mlo;
         const unsigned wl = __reduce_min_sync(FULL, m2_ ? (unsigned)lane : 32u);  // lowest axis index among equal minima
+        const bool bad = __any_sync(FULL, (surv != surv0) | miss);
         // exactly one candidate slot without a separating axis: bit 7 of each NON-zero byte, then "one bit left"
         const unsigned nzb = (((sepbits & 0x7f7f7f7fu) + 0x7f7f7f7fu) | sepbits) & 0x80808080u;
         const unsigned zb = nzb ^ 0x80808080u;  // (no zero byte at all -> no lane is `mine` -> mhi = 0xffffffff)
@@ -394,22 +410,16 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
             }
             __syncwarp();
         }
-        bool ok = check();
+        bool ok = check(std::true_type{});
         while (ok) {
-            // ---- resolution, free body vs fixed body (:171-198) -------------------------------------------------
+            // ---- resolution, free body vs fixed body (:171-174); check() completes it (:180-198) ------------------
             passes++;
-            const double ux = wnx * -1.0, uy = wny * -1.0;                           // :838-839
+            pux = wnx * -1.0; puy = wny * -1.0;                                      // :838-839
             const double sc = mag + kp.eps;                                          // :158
-            const double nvx = ux * sc, nvy = uy * sc;
+            pnvx = pux * sc; pnvy = puy * sc;
 #pragma unroll
-            for (int v = 0; v < NM; v++) { vtx[v] += nvx; vty[v] += nvy; }           // :174
-            if (fma(nvy, nvy, nvx * nvx) > kp.vib_thr) { cpx += nvx; cpy += nvy; }   // :180-181
-            const double vdotN = dot2(cvx, cvy, ux, uy);                             // :183
-            const double cc = kp.ope * vdotN;                                        // :188
-            cvx -= cc * ux;
-            cvy -= cc * uy;
-            heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
-            ok = check();
+            for (int v = 0; v < NM; v++) { vtx[v] += pnvx; vty[v] += pnvy; }         // :174
+            ok = check(std::false_type{});
         }
         if (!__any_sync(FULL, miss)) break;  // (with a stale memo the check above decided nothing: refresh, check again)
     }
