@@ -294,7 +294,11 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     }
     // axis registers of this lane: unit normal, the partner's projection bounds on it and -- for an edge of b -- the
     // exact edge vector the normal was computed from (memo key; NaN = not computed yet).
-    double anx = 0.0, any_ = 0.0, alo2 = 0.0, ahi2 = 0.0, keyx = NAN, keyy = NAN;  // (keys only used by edge lanes)
+    // Lanes without an item carry bounds that decide their result without a flag: (+inf, +inf) in a slot without a
+    // candidate ("separated": hi1 < +inf), (-inf, +inf) in the spare lanes of a candidate slot ("overlap +inf", which never
+    // wins a minimum against a finite overlap).
+    double anx = 0.0, any_ = 0.0, alo2 = active_slot ? -INFINITY : INFINITY, ahi2 = INFINITY;
+    double keyx = NAN, keyy = NAN;  // (keys only used by edge lanes)
     if (active && !freeaxis) {
         const double *g = s.sfix + (v2 + (k - n1)) * 6;
         anx = g[2]; any_ = g[3]; alo2 = g[4]; ahi2 = g[5];
@@ -311,10 +315,18 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     // its result is the plain case (same candidates, one colliding partner, memoised normals valid, finite overlap,
     // watchdog not due); the loop body applies that result and checks again.  Everything else -- a stale edge-normal
     // memo (<2% of the passes) or the hand-over to the general path -- happens outside the hot loop.
-    const bool surv0 = surv;
-    const double tmax = (thr_b > ot) ? thr_b : ot;  // d2 > thr_b && d2 > ot  <=>  d2 > max(thr_b, ot)  (:277, finite radii)
+    // d2 > thr_b && d2 > ot  <=>  d2 > max(thr_b, ot)  (:277, finite radii); lanes without a partner never change
+    const double tmax = partner ? ((thr_b > ot) ? thr_b : ot) : INFINITY;
+    const bool surv0 = partner ? surv : true;
+    // loop constants in registers (an opaque zero keeps them from being re-read from the constant bank every pass)
+    const long long opaque0 = kp.W >> 62;  // W < 2^62
+    const double eps_r = __longlong_as_double(__double_as_longlong(kp.eps) ^ opaque0);
+    const double vthr_r = __longlong_as_double(__double_as_longlong(kp.vib_thr) ^ opaque0);
+    const double ope_r = __longlong_as_double(__double_as_longlong(kp.ope) ^ opaque0);
+    const double hm_r = __longlong_as_double(__double_as_longlong(.5 * m1 * kp.ome2) ^ opaque0);
     bool miss = false;
-    double wnx = 0.0, wny = 0.0, mag = 0.0;
+    double wnx = 0.0, wny = 0.0, nnvx = 0.0, nnvy = 0.0;  // check(): winning axis and the push it asks for
+    bool okv = false;
 
     // (the latency of one warp is also why the statements below are ordered the way they are: the chain
     //  push -> vertices -> projections -> ballot -> three redux -> shuffle comes first, and the rest of a pass --
@@ -347,8 +359,8 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
             double t = lo1; lo1 = lo2; lo2 = t;
             t = hi1; hi1 = hi2; hi2 = t;
         }
-        // lanes of slots without a candidate count as separated: a zero byte of sepbits <=> a colliding partner
-        const bool sep = !active_slot || (active && (hi1 < lo2));                // :820
+        // (lanes without an item: see the sentinel bounds above)  a zero byte of sepbits <=> a colliding partner
+        const bool sep = hi1 < lo2;                                              // :820
         const double cur = hi1 - lo2;                                            // :824
         const unsigned sepbits = __ballot_sync(FULL, sep);
         // first strict minimum in axis order (:827-830) over the 8 lanes of the live slot: three 32-bit redux.sync.min
@@ -357,39 +369,40 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         // so their bit patterns order like unsigned integers; +inf and NaN order above every finite overlap and never
         // win against one (`cur < overlap` with overlap = inf is false for them): if the minimum is one of them the
         // general path takes over.
-        const bool mine = active && ((sepbits & slot_bits) == 0u);
+        const bool mine = (sepbits & slot_bits) == 0u;
         const unsigned long long bits = (unsigned long long)__double_as_longlong(cur);
         const unsigned hiw = (unsigned)(bits >> 32) & 0x7fffffffu, low = (unsigned)bits;
         const unsigned mhi = __reduce_min_sync(FULL, mine ? hiw : 0xffffffffu);
         if constexpr (!decltype(first)::value) {
             // ---- rest of the previous resolution, free body vs fixed body (:180-198) ------------------------------
-            if (fma(pnvy, pnvy, pnvx * pnvx) > kp.vib_thr) { cpx += pnvx; cpy += pnvy; }   // :180-181
+            if (fma(pnvy, pnvy, pnvx * pnvx) > vthr_r) { cpx += pnvx; cpy += pnvy; }       // :180-181
             const double vdotN = dot2(cvx, cvy, pux, puy);                           // :183
-            const double cc = kp.ope * vdotN;                                        // :188
+            const double cc = ope_r * vdotN;                                         // :188
             cvx -= cc * pux;
             cvy -= cc * puy;
-            heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                             // :191,:195
+            heat += hm_r * (vdotN * vdotN);                                          // :191,:195
         }
         const bool m1_ = mine && hiw == mhi;
         const unsigned mlo = __reduce_min_sync(FULL, m1_ ? low : 0xffffffffu);
+        // exactly one candidate slot without a separating axis: its 8 lanes are the `mine` lanes
+        const bool one_live = __popc(__ballot_sync(FULL, mine)) == 8;
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
         const double dx = cpx - ox, dy = cpy - oy;
         const double d2 = fma(dy, dy, dx * dx);
-        surv = partner && !(d2 > tmax);
+        surv = !(d2 > tmax);
         // ---- memo check: edge k of b is (p2.y - p1.y, p1.x - p2.x) (:788-789) ----------------------------------------
         const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
         miss = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
                             ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
+        okv = __all_sync(FULL, !((surv != surv0) | miss) && one_live && mhi < 0x7ff00000u && passes < budget);
+        const double sc = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)) + eps_r;  // :158
         const bool m2_ = m1_ && low == mlo;
         const unsigned wl = __reduce_min_sync(FULL, m2_ ? (unsigned)lane : 32u);  // lowest axis index among equal minima
-        const bool bad = __any_sync(FULL, (surv != surv0) | miss);
-        // exactly one candidate slot without a separating axis: bit 7 of each NON-zero byte, then "one bit left"
-        const unsigned nzb = (((sepbits & 0x7f7f7f7fu) + 0x7f7f7f7fu) | sepbits) & 0x80808080u;
-        const unsigned zb = nzb ^ 0x80808080u;  // (no zero byte at all -> no lane is `mine` -> mhi = 0xffffffff)
-        mag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
         wnx = __shfl_sync(FULL, anx, wl);                                        // the winning axis (:828-830)
         wny = __shfl_sync(FULL, any_, wl);
-        return !bad && (zb & (zb - 1u)) == 0u && mhi < 0x7ff00000u && passes < budget;
+        nnvx = (wnx * -1.0) * sc;                                                // :838-839, :158
+        nnvy = (wny * -1.0) * sc;
+        return okv;
     };
 
     for (;;) {
@@ -415,8 +428,7 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
             // ---- resolution, free body vs fixed body (:171-174); check() completes it (:180-198) ------------------
             passes++;
             pux = wnx * -1.0; puy = wny * -1.0;                                      // :838-839
-            const double sc = mag + kp.eps;                                          // :158
-            pnvx = pux * sc; pnvy = puy * sc;
+            pnvx = nnvx; pnvy = nnvy;
 #pragma unroll
             for (int v = 0; v < NM; v++) { vtx[v] += pnvx; vty[v] += pnvy; }         // :174
             ok = check(std::false_type{});
