@@ -242,8 +242,9 @@ __device__ __forceinline__ bool sat_pair_trial(const ContactSmem &s, int F, pair
 // ---------------------------------------------------------------------------------------------------------------
 template <int N1>  // N1 = exact vertex count of b (3 or 4), or 0 = generic (<= 8 vertices, runtime count)
 __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
-                                             double &heat, int &ncalls, long long &ncalls_total) {
+                                             double &heat, int &ncalls, long long &ncalls_total, bool &done_empty) {
     constexpr int NM = N1 ? N1 : 8;
+    done_empty = false;
     const unsigned FULL = 0xffffffffu;
     const int n1 = N1 ? N1 : kp.nv[b];
     const int v1 = kp.vs[b];
@@ -327,6 +328,7 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     bool miss = false;
     double wnx = 0.0, wny = 0.0, nnvx = 0.0, nnvy = 0.0;  // check(): winning axis and the push it asks for
     bool okv = false;
+    unsigned liveb = 0u;  // lanes of the slots whose pair collides, as of the last check()
 
     // (the latency of one warp is also why the statements below are ordered the way they are: the chain
     //  push -> vertices -> projections -> ballot -> three redux -> shuffle comes first, and the rest of a pass --
@@ -385,7 +387,8 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         const bool m1_ = mine && hiw == mhi;
         const unsigned mlo = __reduce_min_sync(FULL, m1_ ? low : 0xffffffffu);
         // exactly one candidate slot without a separating axis: its 8 lanes are the `mine` lanes
-        const bool one_live = __popc(__ballot_sync(FULL, mine)) == 8;
+        liveb = __ballot_sync(FULL, mine);
+        const bool one_live = __popc(liveb) == 8;
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
         const double dx = cpx - ox, dy = cpy - oy;
         const double d2 = fma(dy, dy, dx * dx);
@@ -434,6 +437,13 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
             ok = check(std::false_type{});
         }
         if (!__any_sync(FULL, miss)) break;  // (with a stale memo the check above decided nothing: refresh, check again)
+    }
+    // The check that ended the loop, when it saw the same candidates and a separating axis for every one of them, IS the
+    // check_collisions() of :234 that returns the empty list (pairs without b have not moved since the general path found
+    // them apart): count it and let update() finish, instead of having the general path find the same nothing again.
+    if (!__any_sync(FULL, surv != surv0) && liveb == 0u && passes < budget) {
+        passes++;
+        done_empty = true;
     }
     ncalls += passes;
     ncalls_total += passes;
@@ -818,14 +828,17 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     const int b = s.hi[0];
                     const long long before = ncalls_total;
                     const int nb = kp.nv[b];
-                    if (nb == 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
-                    else if (nb == 3) fast_resolve<3>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
-                    else if (nb <= 8) fast_resolve<0>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total);
+                    bool done_empty = false;
+                    if (nb == 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, done_empty);
+                    else if (nb == 3) fast_resolve<3>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, done_empty);
+                    else if (nb <= 8) fast_resolve<0>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, done_empty);
                     fast_calls += ncalls_total - before;
                     fast_step += (int)(ncalls_total - before);
+                    if (done_empty) goto end_of_update;  // the fast path made the :234 call that found nothing
                 }
                 continue;
             }
+        end_of_update:
 
             // ---- end of update(): :237-259 -------------------------------------------------------------------
             if (k > 0) {                                       // :248  dt != time_disc
