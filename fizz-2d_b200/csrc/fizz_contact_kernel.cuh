@@ -467,7 +467,13 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
 // FAST = true : the TRAPPED instance -- two narrow-phase items per lane for ILP, 168 registers / 3 CTAs per SM: it owns
 //   the latency-bound tail (tier 3 worlds) and hands a world back after 8 calm timesteps.
 template <bool FAST>
-__global__ void __launch_bounds__(CONTACT_BLOCK, FAST ? 3 : 4)
+#ifndef FIZZ_GEN_CTAS
+#define FIZZ_GEN_CTAS 4
+#endif
+#ifndef FIZZ_FAST_CTAS
+#define FIZZ_FAST_CTAS 3
+#endif
+__global__ void __launch_bounds__(CONTACT_BLOCK, FAST ? FIZZ_FAST_CTAS : FIZZ_GEN_CTAS)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
                const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor) {
     extern __shared__ double smem_c[];
@@ -723,8 +729,17 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         // trials exist while the previous one still had dt > time_tol; lane t >= 1 is a real trial iff
                         // dt_{t-1} > time_tol, which is monotone, so the first `done` lane below is always real
                         if (lane >= 1) {
+                            // :99 only asks whether the largest overlap exceeds COLLISION_TOL: one pair above it decides
+                            // the trial, so the pair that was deepest in the check that just failed goes first
+                            int hm = 0;
+                            for (int h = 1; h < nh; h++)
+                                if (fabs(s.hmag[h]) > fabs(s.hmag[hm])) hm = h;
+                            int pfirst = 0;
+                            for (int p = 0; p < ns; p++)
+                                if (PM_II(s.sp[p]) == s.hi[hm] && PM_JJ(s.sp[p]) == s.hj[hm]) pfirst = p;
                             double mo = 0.0;
-                            for (int p = 0; p < ns; p++) {
+                            for (int q = 0; q < ns && !(mo > kp.coll_tol); q++) {
+                                const int p = (q == 0) ? pfirst : (q <= pfirst ? q - 1 : q);
                                 const pairmeta_t m = s.sp[p];
                                 const int ii = PM_II(m), jj = PM_JJ(m);
                                 double c1x, c1y, c2x = 0.0, c2y = 0.0;
