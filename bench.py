@@ -311,6 +311,13 @@ def run_gpu(args):
                                 "regs": info[k]["regs"], "smem_bytes": info[k]["smem"], "block": info[k]["threads"],
                                 "blocks_per_sm": info[k]["blocks_per_sm"]} for k in prof if prof[k][1]},
                 "dominant_kernel": dom}
+        if "contact" in line["kernels"] and args.mode == "hybrid":
+            # mode hybrid: contact_kernel<false> (the figures above) only runs the chunk that starts at step 0; every
+            # later chunk -- the latency-bound tail -- runs the second instance of the template
+            t = info["trapped"]
+            line["kernels"]["contact"]["instances"] = {
+                "contact_kernel<false> (first chunk)": {"regs": info["contact"]["regs"], "blocks_per_sm": info["contact"]["blocks_per_sm"]},
+                "contact_kernel<true> (all later chunks)": {"regs": t["regs"], "blocks_per_sm": t["blocks_per_sm"]}}
         # ---- CPU baseline + algorithmic work (bounded sample of the same workload) ----------------------------
         ops_per_ws = None
         if not args.no_cpu_baseline:

@@ -197,6 +197,36 @@ def test_relaunch_is_idempotent_for_frozen_worlds(mode):
     assert (sd2[~frozen & (st2 == 0)] == 450).all()
 
 
+@pytest.mark.parametrize("mode", [("hybrid", 256), ("hybrid3", 32), ("hybrid", 5)], ids=["hybrid256", "hybrid3-32", "hybrid5"])
+def test_trapped_worlds_vs_oracle(mode):
+    """The worlds that bound a pass of the benchmark batch -- a square wedged between fixed bodies, ~300 resolve passes per
+    timestep, almost all of them in the single-contact fast path -- plus their neighbours, bit for bit against the
+    oracle; the uncapped default watchdog and a tight one that trips inside the resolve loops."""
+    heavy = [63739, 12860, 5657, 58248, 44270, 36291, 36227, 47547]
+    sel = sorted(set(heavy + [w + d for w in heavy[:4] for d in (-1, 1)]))
+    sc = fz.load_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"))
+    d = np.ascontiguousarray(fz.perturbation_deltas(20260003, 65536, sc.n_free)[sel])
+    for mc, steps in ((4096, 400), (300, 400), (97, 300)):
+        spec = GroupSpec.from_scene(sc, len(sel), d, max_calls=mc)
+        bw = tune(fz.BatchedWorld([spec]), mode)
+        bw.step(steps // 3)
+        bw.step(steps - steps // 3)
+        com, verts, heat, st, sd, calls = bw.com(), bw.vertices(), bw.heat(), bw.status(), bw.steps_done(), bw.calls()
+        k = bw.counters()[0]
+        if mc == 4096:
+            assert calls.max() > 250 * steps * 0.5 and k["fast_path_calls"] > 0.8 * k["contact_calls"], k
+        else:
+            assert (st == fz.ST_CAPPED).any()
+        worlds = [oracle_from_spec(spec, w) for w in range(len(sel))]
+        orc.run_batch(worlds, steps, os.cpu_count() or 1)
+        for w, ow in enumerate(worlds):
+            tag = (mc, sel[w])
+            assert ow.steps_done() == sd[w] and ow.status() == st[w] and ow.total_calls() == calls[w], tag
+            assert np.array_equal(bits(ow.com()), bits(com[w])) and bits(ow.heat()) == bits(heat[w]), tag
+            if st[w] == 0:
+                assert np.array_equal(bits(ow.verts()), bits(verts[w])), tag
+
+
 def test_upload_resets_state():
     bw = fz.BatchedWorld.from_in(scene_file("BOX_1SQUARE"), n_worlds=100, perturb=True, seed=1)
     bw.step(200)
