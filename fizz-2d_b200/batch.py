@@ -374,6 +374,40 @@ class BatchedWorld:
             verts = verts if len(self.groups) == 1 else verts[gi]
         return format_world(g.spec, verts[k])
 
+    def render(self, worlds=None):
+        """Frames of the given worlds (global indices; default: all) as they stand after the last step(): what the
+        reference pipeline would draw from `str(world)` (physics.py:291-301 -> draw.c), rasterised on the GPU straight
+        from the resident state -- vertices never leave the device.  Returns a torch.uint8 tensor [n, H, W] per group
+        that holds any of the worlds (a single tensor when there is one group), rows in the order given."""
+        import torch
+        from . import raster
+        worlds = list(range(self.n_worlds)) if worlds is None else [int(w) for w in worlds]
+        per_group = {}
+        for w in worlds:
+            gi, k = self.locate(w)
+            per_group.setdefault(gi, []).append(k)
+        outs = []
+        for gi in sorted(per_group):
+            g = self.groups[gi]
+            sp = g.spec
+            _lib.check(_lib.load().fizz_vertices(g.handle, C.c_void_p(self._stream_ptr(gi))))
+            if len(self.groups) > 1:
+                torch.cuda.synchronize(g.slab.device)    # groups step on their own streams, torch indexes on its own
+            V = sum(sp.nverts_free)
+            idx = torch.tensor(per_group[gi], dtype=torch.int64, device=g.slab.device)
+            v = g.section("verts", 2 * V)[:, idx]                       # [2V, n]: rows x0, y0, x1, y1, ...
+            verts = v.t().reshape(len(per_group[gi]), V, 2)              # [n, V, 2]
+            fixed = np.array([(max(min(int(p[0]), sp.width - 1), 0), max(min(int(p[1]), sp.height - 1), 0))
+                              for pts in sp.scene.fixed for p in pts], dtype=np.int32).reshape(-1, 2)
+            pts = raster.points_from_vertices(sp.width, sp.height, verts, fixed, device=g.device,
+                                              stream=self._stream_ptr(gi))
+            nverts = list(sp.nverts_free) + [len(pts_) for pts_ in sp.scene.fixed]
+            outs.append(raster.render_points(sp.width, sp.height, nverts, pts, device=g.device,
+                                             stream=self._stream_ptr(gi)))
+        if len(self.groups) > 1:
+            torch.cuda.synchronize(self.groups[0].slab.device)
+        return outs[0] if len(self.groups) == 1 else outs
+
     def locate(self, i):
         """(group index, index inside the group) of global world i."""
         if self._where is None:

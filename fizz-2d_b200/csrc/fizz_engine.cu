@@ -11,6 +11,7 @@
 #include "fizz_ballistic_kernel.cuh"
 #include "fizz_common.cuh"
 #include "fizz_contact_kernel.cuh"
+#include "fizz_raster.cuh"
 #include "fizz_thread_kernel.cuh"
 
 #include <cstdio>
@@ -711,6 +712,52 @@ int fizz_fp64_peak(int device, int32_t iters, double *tflops, double *ms_out) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    return FIZZ_OK;
+}
+
+int fizz_raster_frames(int device, int32_t width, int32_t height, int64_t n_frames, int32_t n_polygons,
+                       const int32_t *nverts, const int32_t *points_dev, uint8_t *gray_dev, void *stream) {
+    if (width < 1 || height < 1 || n_frames < 0 || n_polygons < 0 || n_polygons > FIZZ_RASTER_MAX_POLYGONS)
+        return fail(FIZZ_E_ARG, "fizz_raster_frames: bad size (1 <= width, height; 0 <= polygons <= 64)");
+    if (n_frames == 0) return FIZZ_OK;
+    if ((n_polygons && (!nverts || !points_dev)) || !gray_dev) return fail(FIZZ_E_ARG, "fizz_raster_frames: null argument");
+    if (n_frames > 0x7fffffffLL) return fail(FIZZ_E_ARG, "fizz_raster_frames: more than 2^31-1 frames in one call");
+    RasterParams rp;
+    rp.W = width; rp.H = height; rp.RW = (width + 31) / 32;
+    rp.n_poly = n_polygons; rp.n_points = 0;
+    for (int p = 0; p < n_polygons; p++) {
+        if (nverts[p] < 1) return fail(FIZZ_E_ARG, "fizz_raster_frames: polygon without vertices");
+        rp.nverts[p] = nverts[p];
+        rp.n_points += nverts[p];
+    }
+    rp.points = points_dev; rp.gray = gray_dev;
+    if (rp.RW > 32) return fail(FIZZ_E_ARG, "fizz_raster_frames: canvas wider than 1024 pixels (a row is one warp of words)");
+    const size_t smem = 2 * sizeof(unsigned) * (size_t)height * rp.RW;
+    if (smem > 227 * 1024) return fail(FIZZ_E_ARG, "fizz_raster_frames: frame too large for the shared memory of an SM");
+    CU(cudaSetDevice(device));
+    static size_t raised = 0;
+    if (smem > 48 * 1024 && smem > raised) {
+        CU(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raised = smem;
+    }
+    raster_kernel<<<(unsigned)n_frames, RASTER_BLOCK, smem, (cudaStream_t)stream>>>(rp);
+    CU(cudaGetLastError());
+    return FIZZ_OK;
+}
+
+int fizz_points_from_vertices(int device, int32_t width, int32_t height, int64_t n_frames, int32_t n_free_points,
+                              const double *verts_dev, int32_t n_fixed_points, const int32_t *fixed_points_dev,
+                              int32_t *points_dev, void *stream) {
+    if (width < 1 || height < 1 || n_frames < 0 || n_free_points < 0 || n_fixed_points < 0)
+        return fail(FIZZ_E_ARG, "fizz_points_from_vertices: bad size");
+    const long long total = (long long)n_frames * (n_free_points + n_fixed_points);
+    if (total == 0) return FIZZ_OK;
+    if ((n_free_points && !verts_dev) || (n_fixed_points && !fixed_points_dev) || !points_dev)
+        return fail(FIZZ_E_ARG, "fizz_points_from_vertices: null argument");
+    CU(cudaSetDevice(device));
+    points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        verts_dev, fixed_points_dev, points_dev, n_frames, n_free_points, n_fixed_points, width, height);
+    CU(cudaGetLastError());
     return FIZZ_OK;
 }
 

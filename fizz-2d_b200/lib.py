@@ -69,7 +69,12 @@ EXPORTS = {
     "fizz_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "fizz_profile_read": (C.c_int, [C.c_void_p, dp, lp, C.c_int32]),
     "fizz_fp64_peak": (C.c_int, [C.c_int, C.c_int32, dp, dp]),
+    "fizz_raster_frames": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int64, C.c_int32, ip, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "fizz_points_from_vertices": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
 }
+RASTER_MAX_POLYGONS = 64
 
 _lib = None
 

@@ -208,6 +208,29 @@ int fizz_counters(FizzGroup *g, int64_t *out4, int32_t reset, void *stream);
  * dependent-chain DFMA rounds on every SM of `device` and returns achieved TFLOP/s (FMA = 2 flops). */
 int fizz_fp64_peak(int device, int32_t iters, double *tflops, double *ms);
 
+/* ---- batched rasteriser ------------------------------------------------------------------
+ * Replaces the reference's only native program, /root/reference/src/draw.c (`./draw START END`: spec_to_image
+ * :189-221, draw_polygon :116-157, draw_line :87-114, fill_shape :159-187) and the grey scaling of
+ * png_util.c:238-262, for a BATCH of frames that share one topology (the frames of one world over time, or of many
+ * worlds of a group at one time).  One CTA per frame; the canvas lives in shared memory as a bitmap.
+ *
+ * points_dev: device, int32 [n_frames][n_points][2] = (x, y) of every polygon vertex in file order, n_points =
+ * sum(nverts[0..n_polygons-1]) (host array).  gray_dev: device, uint8 [n_frames][height][width], 255 = FILLED, 0 = EMPTY
+ * (the value the reference writes to all three channels of its 8-bit RGB PNG).  Fails (FIZZ_E_ARG) when width > 1024
+ * (a row of the bitmap is one warp of 32-bit words) or when the two bitmaps of a frame do not fit the shared memory of
+ * an SM: 2 * height * ceil(width/32) * 4 bytes <= 227 KB (the reference's largest scene is 1010 x 710: 182 KB). */
+#define FIZZ_RASTER_MAX_POLYGONS 64
+int fizz_raster_frames(int device, int32_t width, int32_t height, int64_t n_frames, int32_t n_polygons,
+                       const int32_t *nverts, const int32_t *points_dev, uint8_t *gray_dev, void *stream);
+
+/* Point.__str__ (physics.py:600-606) on the device: verts_dev = double [n_frames][n_free_points][2] (point.pos of the
+ * free polygons) -> int() truncation, clamp to [0,width-1] x [0,height-1]; the n_fixed_points integer points of the
+ * fixed polygons (fixed_points_dev, int32 [n_fixed_points][2], may be NULL when 0) are appended to every frame, the
+ * order World.__str__ (physics.py:291-301) prints.  points_dev: int32 [n_frames][n_free_points + n_fixed_points][2]. */
+int fizz_points_from_vertices(int device, int32_t width, int32_t height, int64_t n_frames, int32_t n_free_points,
+                              const double *verts_dev, int32_t n_fixed_points, const int32_t *fixed_points_dev,
+                              int32_t *points_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
