@@ -42,6 +42,30 @@ def test_config3_full_size_properties():
         assert ow.total_calls() == calls[w], w
 
 
+def test_config3_critical_worlds_full_length():
+    """The worlds whose sequential chains bound a pass of the benchmark (the heaviest of seed 20260003: up to 3.3e6
+    check_collisions() in 10 000 timesteps, 83-91 % of them in the single-contact fast path, most of the rest halving
+    trials) over the benchmark's full
+    10 000 timesteps, bit for bit against the oracle -- state, heat, call counts."""
+    from fizz2d_b200.batch import GroupSpec
+    heavy = [63739, 12860, 58248, 44270, 36291, 36227, 47547, 29797]
+    sc = fz.load_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"))
+    d = np.ascontiguousarray(fz.perturbation_deltas(20260003, 65536, sc.n_free)[heavy])
+    spec = GroupSpec.from_scene(sc, len(heavy), d)
+    bw = fz.BatchedWorld([spec])
+    bw.step(10000)
+    com, heat, st, sd, calls, verts = bw.com(), bw.heat(), bw.status(), bw.steps_done(), bw.calls(), bw.vertices()
+    k = bw.counters()[0]
+    assert calls.max() > 3_000_000 and k["fast_path_calls"] > 0.8 * k["contact_calls"]
+    worlds = [oracle_from_spec(spec, w) for w in range(len(heavy))]
+    orc.run_batch(worlds, 10000, os.cpu_count() or 1)
+    for w, ow in enumerate(worlds):
+        assert ow.steps_done() == sd[w] == 10000 and ow.status() == st[w] == 0, heavy[w]
+        assert ow.total_calls() == calls[w], heavy[w]
+        assert np.array_equal(bits(ow.com()), bits(com[w])) and bits(ow.heat()) == bits(heat[w]), heavy[w]
+        assert np.array_equal(bits(ow.verts()), bits(verts[w])), heavy[w]
+
+
 def test_config4_full_size_properties():
     """262144 mixed worlds (2CHAMBERS / STACKEDCHAMBERS, seed 20260004) x 300 steps in the throughput mode:
     a random sample equals the oracle; energy is conserved or dissipated, never created."""
