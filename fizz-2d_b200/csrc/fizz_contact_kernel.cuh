@@ -4,7 +4,7 @@
 // kernel stopped at a non-empty broad phase, plus step 0 of every world).  The world's state (com, snapshot,
 // polar offsets, vertices, contact list) lives in the warp's slice of shared memory for the whole launch; the
 // fixed scene is staged once per CTA.  A pass over a batch is bounded by the SEQUENTIAL depth of its worst world
-// (30 halving trials + fallback + up to ~100 resolve passes per timestep for a trapped body), so
+// (30 halving trials + fallback + up to ~300 resolve passes per timestep for a trapped body), so
 // everything here is organised around the latency of one check_collisions() (physics.py:262-289):
 //   * broad phase: lanes stride over a packed pair table, __ballot compacts the survivors in reference order;
 //   * narrow phase: lanes map to (pair, axis) items of polypoly_collision (:765-840) in fixed-width slots, two
@@ -16,7 +16,9 @@
 //     (every trial restarts from the start-of-step state, so they are independent) and a __ballot picks the
 //     first trial that ends the loop;
 //   * resolution (:142-233) walks the list in order; vertices are pushed lane-parallel, the centre of mass by
-//     lane 0.
+//     lane 0;
+//   * a resolve loop that keeps returning ONE tuple (free body, fixed body) -- the trapped-body pattern that bounds a
+//     pass -- continues in fast_resolve<N>: state in registers, one branch per pass (see there).
 #pragma once
 
 #include <type_traits>
