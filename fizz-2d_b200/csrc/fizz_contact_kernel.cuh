@@ -477,7 +477,8 @@ template <bool FAST>
 #endif
 __global__ void __launch_bounds__(CONTACT_BLOCK, FAST ? FIZZ_FAST_CTAS : FIZZ_GEN_CTAS)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
-               const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor) {
+               const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor,
+               unsigned long long count_cap = ~0ull) {
     extern __shared__ double smem_c[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -510,7 +511,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
     const unsigned slot_mask = (SW == 32 ? FULL : ((1u << SW) - 1u)) << (my_slot * SW);
 
     const long long Wp = kp.Wp;
-    const unsigned long long count = *count_ptr;
+    const unsigned long long count = min(*count_ptr, count_cap);  // (a capped list: classify_kernel's `cap`)
     const bool speculate = (kp.trace == nullptr);  // the contact trace needs every trial's tuples: sequential then
 
     for (;;) {
@@ -925,9 +926,12 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 // Work list for the contact kernel: every running world that has not reached the chunk target.
 // `calls` / rate window: only worlds whose lifetime average of check_collisions() per timestep lies in [rate_lo,
 // rate_hi) are taken (pass calls = nullptr to take all): lets the host append the heaviest worlds first.
-__global__ void classify_kernel(const long long *status, const long long *steps, const long long *tier, long long W,
+// `mark` >= 0: the selected worlds get tier = mark (runner mode: 4 = "owned by a runner launch", which keeps every other
+// kernel of the pipeline away from them until the runner has stored them again).
+__global__ void classify_kernel(const long long *status, const long long *steps, long long *tier, long long W,
                                 long long target, long long tier_lo, long long tier_hi, const long long *calls,
-                                long long rate_lo, long long rate_hi, long long *list, unsigned long long *count) {
+                                long long rate_lo, long long rate_hi, long long *list, unsigned long long *count,
+                                long long mark = -1, unsigned long long cap = ~0ull) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool lag = (w < W) && status[w] == 0 && steps[w] < target && tier[w] >= tier_lo && tier[w] <= tier_hi;
     if (lag && calls) {
@@ -940,7 +944,11 @@ __global__ void classify_kernel(const long long *status, const long long *steps,
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(b));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (lag) list[base + __popc(b & ((1u << lane) - 1u))] = w;
+    const unsigned long long idx = base + __popc(b & ((1u << lane) - 1u));
+    if (lag && idx < cap) {       // (beyond `cap` a world is neither listed nor marked: the count is clamped by the reader)
+        list[idx] = w;
+        if (mark >= 0) tier[w] = mark;
+    }
 }
 
 // Derived vertices for worlds whose point.pos are not explicit state: |r|cos(phi) + com.x, |r|sin(phi) + com.y

@@ -15,6 +15,7 @@
 #include "fizz_thread_kernel.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,6 +78,9 @@ int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// dynamic shared memory of a runner launch: enough that a runner CTA has its SM to itself (see fizz_step)
+constexpr size_t RUNNER_SMEM = 200 * 1024;
 
 struct KernelInfo {
     cudaFuncAttributes attr;
@@ -159,6 +163,14 @@ struct FizzGroup {
     long long *sched_list, *sched_list2;
     cudaStream_t side;          // library-owned stream: the trapped instance runs beside the general one
     cudaEvent_t ev_fork, ev_join;
+    // runner mode: trapped worlds leave the chunk pipeline and are stepped to the end of the fizz_step() call by their
+    // own launch of the latency-tuned instance, one library-owned stream per launch (no launch waits for another one)
+    static const int NR = 16;   // runner launches per fizz_step() call (one stream each; further boundaries launch none)
+    cudaStream_t rstream[NR];
+    cudaEvent_t rdone[NR];
+    long long *rlist;            // [NR][rcap] work lists (engine-owned, outside the caller's slab)
+    long long rcap;              // entries per list = one warp per world, one CTA per SM
+    unsigned long long *rcount;  // [NR][2] count, cursor
     unsigned long long *sched_count;  // [0] = count, [1] = cursor
     unsigned char *vbody_dev;
     // optional per-kernel timing (fizz_set_profiling)
@@ -272,6 +284,8 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     g->mode = FIZZ_MODE_HYBRID; g->chunk = 256;
     g->profile = false; g->ev_used = 0;
     g->side = nullptr; g->ev_fork = nullptr; g->ev_join = nullptr;
+    g->rlist = nullptr; g->rcount = nullptr;
+    for (int i = 0; i < FizzGroup::NR; i++) { g->rstream[i] = nullptr; g->rdone[i] = nullptr; }
     for (int i = 0; i < 3; i++) { g->prof_ms[i] = 0.0; g->prof_launches[i] = 0; }
     KParams &kp = g->kp;
     double *s = g->slab;
@@ -347,7 +361,10 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     {
         static size_t current_general = 0, current_trapped = 0;
         e = raise_dynamic_smem(contact_kernel<false>, g->contact_smem, &current_general);
-        if (e == cudaSuccess) e = raise_dynamic_smem(contact_kernel<true>, g->contact_smem, &current_trapped);
+        // (runner launches ask for RUNNER_SMEM so that nothing else becomes resident on the SM that hosts them)
+        if (e == cudaSuccess)
+            e = raise_dynamic_smem(contact_kernel<true>, g->contact_smem > RUNNER_SMEM ? g->contact_smem : RUNNER_SMEM,
+                                   &current_trapped);
     }
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&g->contact_ki.attr, contact_kernel<false>);
     if (e == cudaSuccess)
@@ -364,7 +381,14 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
-    if (e != cudaSuccess) { delete g; return cuda_fail(e, "side stream setup"); }
+    for (int i = 0; i < FizzGroup::NR && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&g->rstream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->rdone[i], cudaEventDisableTiming);
+    }
+    g->rcap = (long long)g->sm_count * CONTACT_WARPS;
+    if (e == cudaSuccess) e = cudaMalloc(&g->rlist, sizeof(long long) * (size_t)FizzGroup::NR * (size_t)g->rcap);
+    if (e == cudaSuccess) e = cudaMalloc(&g->rcount, sizeof(unsigned long long) * 2 * FizzGroup::NR);
+    if (e != cudaSuccess) { fizz_group_destroy(g); return cuda_fail(e, "side stream setup"); }
     *out = g;
     return FIZZ_OK;
 }
@@ -375,6 +399,12 @@ int fizz_group_destroy(FizzGroup *g) {
         if (g->ev_fork) cudaEventDestroy(g->ev_fork);
         if (g->ev_join) cudaEventDestroy(g->ev_join);
         if (g->side) cudaStreamDestroy(g->side);
+        for (int i = 0; i < FizzGroup::NR; i++) {
+            if (g->rdone[i]) cudaEventDestroy(g->rdone[i]);
+            if (g->rstream[i]) cudaStreamDestroy(g->rstream[i]);
+        }
+        if (g->rlist) cudaFree(g->rlist);
+        if (g->rcount) cudaFree(g->rcount);
     }
     delete g;
     return FIZZ_OK;
@@ -406,7 +436,7 @@ int fizz_profile_read(FizzGroup *g, double *ms, int64_t *launches, int32_t reset
 
 int fizz_set_tuning(FizzGroup *g, int32_t mode, int64_t chunk_steps) {
     if (!g) return fail(FIZZ_E_ARG, "fizz_set_tuning: null group");
-    if (mode != FIZZ_MODE_HYBRID && mode != FIZZ_MODE_THREAD && mode != FIZZ_MODE_HYBRID3)
+    if (mode != FIZZ_MODE_HYBRID && mode != FIZZ_MODE_THREAD && mode != FIZZ_MODE_HYBRID3 && mode != FIZZ_MODE_HYBRID_SYNC)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: unknown mode");
     if (mode == FIZZ_MODE_THREAD && !g->thread_ok)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: thread mode does not fit in shared memory for this topology");
@@ -495,6 +525,23 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     const long long kfull = (long long)g->sm_count * g->contact_ki.blocks_per_sm;
     const long long tfull = (long long)g->sm_count * g->trapped_ki.blocks_per_sm;
     const dim3 kgrid((unsigned)(kneed < kfull ? kneed : kfull)), tgrid((unsigned)(kneed < tfull ? kneed : tfull));
+    // runner mode (FIZZ_MODE_HYBRID): at a chunk boundary the worlds flagged "trapped" (tier 3) are handed to their own
+    // launch of the latency-tuned instance, on a library-owned stream that is idle, with the END of this call as target;
+    // they are marked tier 4 on the way, which keeps the chunk pipeline away from them.  Nothing waits for a runner
+    // before the join below, and a runner waits for nothing.  Short calls (per-timestep stepping) do not bother.
+    const long long final_target = g->target + n_steps;
+#ifdef FIZZ_RUNNER_DEBUG
+    cudaEvent_t d0 = nullptr;
+    cudaEventCreate(&d0);
+    cudaEventRecord(d0, st);
+#endif
+    const bool runners = (g->mode == FIZZ_MODE_HYBRID) && n_steps >= 128;
+    bool rused[FizzGroup::NR] = {};
+    int rnext = 0;
+    const unsigned long long runner_cap = (unsigned long long)g->rcap;  // one CTA per SM, all resident
+    const dim3 rgrid((unsigned)(kneed < g->sm_count ? kneed : g->sm_count));
+    const long long runner_rate = 48;   // check_collisions() per timestep, lifetime average
+    const size_t runner_smem = g->contact_smem > RUNNER_SMEM ? g->contact_smem : RUNNER_SMEM;
     int64_t nchunk = 0;
     for (int64_t done = 0; done < n_steps; nchunk++) {
         // chunk length: the tuned value for the first chunks (contact episodes are short and early), then doubling every
@@ -518,13 +565,39 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         }
         cudaEvent_t eb = g->profile ? next_event(g, st) : nullptr;
         CU(cudaMemsetAsync(g->sched_count, 0, 4 * sizeof(unsigned long long), st));
-        if (g->mode == FIZZ_MODE_HYBRID) {
+        if (g->mode == FIZZ_MODE_HYBRID || g->mode == FIZZ_MODE_HYBRID_SYNC) {
+            // (nothing is flagged before the first chunk has run; a stream is used once per call: a second launch on it
+            //  would wait for the first, which runs to the end of the call.  Every call ends with a join, so the streams
+            //  are free again when the next call's launches reach the device -- no host-side query, the host may be
+            //  many calls ahead of the GPU)
+            int slot = -1;
+            if (runners && g->target > c && rnext < FizzGroup::NR) slot = rnext++;
+            if (slot >= 0) {
+                unsigned long long *rc = g->rcount + 2 * slot;
+                long long *rl = g->rlist + (size_t)slot * (size_t)g->rcap;
+                CU(cudaMemsetAsync(rc, 0, 2 * sizeof(unsigned long long), st));
+                // candidates: flagged trapped AND heavy over their lifetime (>= 48 check_collisions() per timestep: the
+                // heaviest ~0.3 % of config 3) -- half of all worlds see one long resolve loop early on, and a runner
+                // list longer than the grid would make the worlds at its end wait instead of run (hence also the cap).
+                // A runner CTA asks for RUNNER_SMEM of shared memory, i.e. for an SM of its own: measured on config 3,
+                // sharing SMs with the chunk pipeline makes the longest chain 0-20 % slower depending on where it lands
+                // (540-640 ms per pass), alone it is 545-560 ms every time (no runners: 580-620)
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, kp.calls,
+                                                       runner_rate, 1LL << 40, rl, rc, 4, runner_cap);
+                CU(cudaEventRecord(g->ev_fork, st));
+                CU(cudaStreamWaitEvent(g->rstream[slot], g->ev_fork, 0));
+                KParams kr = kp;
+                kr.target_steps = final_target;
+                contact_kernel<true><<<rgrid, CONTACT_BLOCK, runner_smem, g->rstream[slot]>>>(kr, rl, rc, rc + 1, runner_cap);
+                rused[slot] = true;
+                g->launches += 2;
+            }
             // latency-tuned: ONE instance (two narrow-phase items per lane, 3 CTAs/SM) steps every lagging world, so the
             // world with the longest chain of resolve passes never waits for anything
             // (work list in world order: measured -- grouping the trapped worlds at the head of the list, or sorting them
             //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
             classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, nullptr, 0, 1,
-                                                   g->sched_list, g->sched_count);
+                                                   g->sched_list, g->sched_count);   // (tier 4: owned by a runner)
             // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
             // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
             if (g->target == c)
@@ -560,6 +633,47 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         g->launches += 6;
         done += c;
     }
+    bool any = false;
+#ifdef FIZZ_RUNNER_DEBUG
+    cudaEvent_t d_main = nullptr, d_run[FizzGroup::NR] = {};
+    cudaEventCreate(&d_main);
+    cudaEventRecord(d_main, st);
+    for (int i = 0; i < FizzGroup::NR; i++)
+        if (rused[i]) { cudaEventCreate(&d_run[i]); cudaEventRecord(d_run[i], g->rstream[i]); }
+#endif
+    for (int i = 0; i < FizzGroup::NR; i++)
+        if (rused[i]) {
+            CU(cudaEventRecord(g->rdone[i], g->rstream[i]));
+            CU(cudaStreamWaitEvent(st, g->rdone[i], 0));
+            any = true;
+        }
+    if (any) {
+        // whatever is still short of the target (a world flagged trapped by the last chunks, when no stream was idle)
+        CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
+        classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 0, 4, nullptr, 0, 1,
+                                               g->sched_list, g->sched_count);
+        kp.target_steps = final_target;
+        contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                            g->sched_count + 1);
+        CU(cudaGetLastError());
+        g->launches += 2;
+    }
+#ifdef FIZZ_RUNNER_DEBUG
+    {
+        cudaStreamSynchronize(st);
+        float t = 0;
+        cudaEventElapsedTime(&t, d0, d_main);
+        fprintf(stderr, "[runner debug] main pipeline done at %.1f ms;", t);
+        for (int i = 0; i < FizzGroup::NR; i++)
+            if (d_run[i]) { cudaEventElapsedTime(&t, d0, d_run[i]); fprintf(stderr, " runner%d %.1f", i, t); cudaEventDestroy(d_run[i]); }
+        unsigned long long rc[2 * FizzGroup::NR];
+        cudaMemcpy(rc, g->rcount, sizeof(rc), cudaMemcpyDeviceToHost);
+        fprintf(stderr, " | list sizes:");
+        for (int i = 0; i < FizzGroup::NR; i++) fprintf(stderr, " %llu", rc[2 * i]);
+        fprintf(stderr, "\n");
+        cudaEventDestroy(d_main); cudaEventDestroy(d0);
+    }
+#endif
     return FIZZ_OK;
 }
 

@@ -36,8 +36,11 @@ extern "C" {
 #define FIZZ_E_STATE (-3)   /* call sequence error (e.g. step before upload) */
 
 /* execution modes (fizz_set_tuning) */
-#define FIZZ_MODE_HYBRID 1  /* ballistic thread-per-world kernel + ONE latency-tuned warp-per-world contact kernel:
-                               best when a few trapped worlds bound the pass (default)                        */
+#define FIZZ_MODE_HYBRID 1  /* ballistic thread-per-world kernel + latency-tuned warp-per-world contact kernel per chunk
+                               of timesteps; worlds found trapped leave the chunk pipeline and are stepped to the end
+                               of the fizz_step() call by "runner" launches on library-owned streams, so that the
+                               longest sequential chain never waits at a chunk boundary (default)             */
+#define FIZZ_MODE_HYBRID_SYNC 3 /* the same without runners: every world stops at every chunk boundary      */
 #define FIZZ_MODE_THREAD 0  /* one thread-per-world kernel with the full semantics                        */
 #define FIZZ_MODE_HYBRID3 2 /* throughput-tuned: adds a thread-per-world "separation prover" tier and splits the contact
                                kernel into a compact high-occupancy general instance and a trapped instance that run

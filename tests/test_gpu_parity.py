@@ -16,7 +16,8 @@ from helpers import bits, contact_rows, oracle_from_spec, orc
 pytestmark = pytest.mark.gpu
 
 # execution strategies (results must never depend on them): hybrid = ballistic thread-per-world kernel + warp-per-
-# world contact kernel per chunk of timesteps; thread = one thread-per-world kernel with the full semantics
+# world contact kernel per chunk of timesteps, trapped worlds on runner launches that skip the chunk boundaries (calls of
+# >= 128 timesteps); hybrid_sync = without runners; thread = one thread-per-world kernel with the full semantics
 MODES = [("hybrid", 256), ("hybrid3", 7), ("thread", 1)]
 
 
@@ -197,7 +198,8 @@ def test_relaunch_is_idempotent_for_frozen_worlds(mode):
     assert (sd2[~frozen & (st2 == 0)] == 450).all()
 
 
-@pytest.mark.parametrize("mode", [("hybrid", 256), ("hybrid3", 32), ("hybrid", 5)], ids=["hybrid256", "hybrid3-32", "hybrid5"])
+@pytest.mark.parametrize("mode", [("hybrid", 256), ("hybrid3", 32), ("hybrid", 5), ("hybrid_sync", 64)],
+                         ids=["hybrid256", "hybrid3-32", "hybrid5", "hybrid_sync64"])
 def test_trapped_worlds_vs_oracle(mode):
     """The worlds that bound a pass of the benchmark batch -- a square wedged between fixed bodies, ~300 resolve passes per
     timestep, almost all of them in the single-contact fast path -- plus their neighbours, bit for bit against the
@@ -227,6 +229,24 @@ def test_trapped_worlds_vs_oracle(mode):
                 assert np.array_equal(bits(ow.verts()), bits(verts[w])), tag
 
 
+def test_runner_mode_call_patterns():
+    """Runner launches only exist inside fizz_step() calls of >= 128 timesteps and end with them: any split of a run
+    into calls -- long ones that use runners, short ones that do not, a mix -- ends in the same bits as one call and as
+    the pipeline without runners."""
+    def run(mode, chunk, calls):
+        bw = tune(fz.BatchedWorld.from_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=4096, perturb=True,
+                                          seed=20260003, max_calls=512), (mode, chunk))
+        for c in calls:
+            bw.step(c)
+        return bw.com(), bw.heat(), bw.status(), bw.steps_done(), bw.calls(), bw.vertices()
+    ref = run("hybrid_sync", 256, (1500,))
+    for mode, chunk, calls in (("hybrid", 64, (1500,)), ("hybrid", 32, (127, 128, 129, 1116)), ("hybrid", 256, (700, 1, 799)),
+                               ("hybrid", 17, (300, 300, 300, 300, 300))):
+        got = run(mode, chunk, calls)
+        for x, y in zip(ref, got):
+            assert np.array_equal(bits(x) if x.dtype == np.float64 else x, bits(y) if y.dtype == np.float64 else y), (mode, chunk, calls)
+
+
 def test_upload_resets_state():
     bw = fz.BatchedWorld.from_in(scene_file("BOX_1SQUARE"), n_worlds=100, perturb=True, seed=1)
     bw.step(200)
@@ -253,7 +273,7 @@ def test_snapshot_restore_replays_bit_exactly():
 def test_hybrid_equals_thread_mode_large_batch():
     """The two independent kernel families agree bit for bit on 8192 perturbed RAMPWORLD worlds x 600 steps."""
     outs = []
-    for mode in (("hybrid", 128), ("hybrid3", 32), ("thread", 1)):
+    for mode in (("hybrid", 128), ("hybrid_sync", 256), ("hybrid3", 32), ("thread", 1)):
         bw = tune(fz.BatchedWorld.from_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=8192, perturb=True,
                                           seed=20260003, max_calls=128), mode)
         bw.step(600)
