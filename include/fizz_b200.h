@@ -160,7 +160,10 @@ int fizz_upload(FizzGroup *g, const double *pos, const double *vel, const double
 /* Advance every running world by n_steps World.update() calls (physics.py:76-259); stands in for the loop
  * `for t in range(N): plane.update()` of main.py:97-98.  Asynchronous on `stream`, no host synchronisation.
  * Hybrid mode: per chunk of timesteps one ballistic launch (thread per world, registers only), one work-list
- * launch and one persistent contact launch (warp per world).  Thread mode: one launch for all n_steps. */
+ * launch and one persistent contact launch (warp per world).  Thread mode: one launch for all n_steps.
+ * FIZZ_MODE_HYBRID, n_steps >= 128: worlds found trapped are additionally handed to "runner" launches on streams the
+ * library owns; each of them is forked from `stream` by an event and joined back into `stream` before the call
+ * returns, so whatever the caller enqueues on `stream` afterwards sees every world at its target. */
 int fizz_step(FizzGroup *g, int64_t n_steps, void *stream);
 
 /* Streaming variant: like fizz_step, but before every timestep t the World.energy() row of EVERY world
