@@ -247,6 +247,19 @@ def test_runner_mode_call_patterns():
             assert np.array_equal(bits(x) if x.dtype == np.float64 else x, bits(y) if y.dtype == np.float64 else y), (mode, chunk, calls)
 
 
+def test_runner_mode_mixed_groups():
+    """Several groups step on their own streams, each with its own runner streams: same bits as without runners."""
+    paths = [scene_file("2CHAMBERS_3BALLS"), scene_file("STACKEDCHAMBERS_1SQUARE"), scene_file("RAMPWORLD_2TRIANGLES_5SQUARES")]
+    outs = []
+    for mode in (("hybrid_sync", 256), ("hybrid", 32)):
+        bw = tune(fz.BatchedWorld.from_mixed(paths, 6000, seed=20260004, max_calls=384), mode)
+        bw.step(450)
+        bw.step(200)
+        outs.append((bw.heat(), bw.status(), bw.steps_done(), bw.calls(), np.concatenate([c.ravel() for c in bw.com()])))
+    for x, y in zip(*outs):
+        assert np.array_equal(bits(x) if x.dtype == np.float64 else x, bits(y) if y.dtype == np.float64 else y)
+
+
 def test_upload_resets_state():
     bw = fz.BatchedWorld.from_in(scene_file("BOX_1SQUARE"), n_worlds=100, perturb=True, seed=1)
     bw.step(200)
