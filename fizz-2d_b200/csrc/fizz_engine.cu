@@ -169,7 +169,8 @@ struct FizzGroup {
     cudaStream_t rstream[NR];
     cudaEvent_t rdone[NR];
     long long *rlist;            // [NR][rcap] work lists (engine-owned, outside the caller's slab)
-    long long rcap;              // entries per list = one warp per world, one CTA per SM
+    long long rcap;              // entries per list: one warp per world, one CTA per SM, a third of the SMs at most
+                                 // (runner CTAs keep their SMs to themselves: the chunk pipeline needs the rest)
     unsigned long long *rcount;  // [NR][2] count, cursor
     unsigned long long *sched_count;  // [0] = count, [1] = cursor
     unsigned char *vbody_dev;
@@ -385,7 +386,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
         e = cudaStreamCreateWithFlags(&g->rstream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->rdone[i], cudaEventDisableTiming);
     }
-    g->rcap = (long long)g->sm_count * CONTACT_WARPS;
+    g->rcap = (long long)(g->sm_count / 3 > 0 ? g->sm_count / 3 : 1) * CONTACT_WARPS;  // a third of the SMs at most
     if (e == cudaSuccess) e = cudaMalloc(&g->rlist, sizeof(long long) * (size_t)FizzGroup::NR * (size_t)g->rcap);
     if (e == cudaSuccess) e = cudaMalloc(&g->rcount, sizeof(unsigned long long) * 2 * FizzGroup::NR);
     if (e != cudaSuccess) { fizz_group_destroy(g); return cuda_fail(e, "side stream setup"); }
@@ -538,7 +539,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     const bool runners = (g->mode == FIZZ_MODE_HYBRID) && n_steps >= 128;
     bool rused[FizzGroup::NR] = {};
     int rnext = 0;
-    const unsigned long long runner_cap = (unsigned long long)g->rcap;  // one CTA per SM, all resident
+    const unsigned long long runner_cap = (unsigned long long)g->rcap;  // all resident at once, see FizzGroup::rcap
     const dim3 rgrid((unsigned)(kneed < g->sm_count ? kneed : g->sm_count));
     const long long runner_rate = 48;   // check_collisions() per timestep, lifetime average
     const size_t runner_smem = g->contact_smem > RUNNER_SMEM ? g->contact_smem : RUNNER_SMEM;
@@ -582,8 +583,11 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                 // A runner CTA asks for RUNNER_SMEM of shared memory, i.e. for an SM of its own: measured on config 3,
                 // sharing SMs with the chunk pipeline makes the longest chain 0-20 % slower depending on where it lands
                 // (540-640 ms per pass), alone it is 545-560 ms every time (no runners: 580-620)
+                // (two passes so that the very heaviest get their slots first when the cap bites)
                 classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, kp.calls,
-                                                       runner_rate, 1LL << 40, rl, rc, 4, runner_cap);
+                                                       3 * runner_rate, 1LL << 40, rl, rc, 4, runner_cap);
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, kp.calls,
+                                                       runner_rate, 3 * runner_rate, rl, rc, 4, runner_cap);
                 CU(cudaEventRecord(g->ev_fork, st));
                 CU(cudaStreamWaitEvent(g->rstream[slot], g->ev_fork, 0));
                 KParams kr = kp;
