@@ -726,23 +726,18 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 if (maxov > kp.coll_tol && dt > kp.time_tol) {  // :99
                     if (k == 0 && speculate) {
                         // ---- speculative halving: lane t evaluates trial t (dt / 2^t) on its own -----------------
+                        // dt / 2 / 2 ... (:106, `lane` times) is dt * 2^-lane exactly as long as nothing gets subnormal
                         double dtt = dt;
-                        for (int t = 0; t < lane; t++) dtt = dtt / 2;   // exact, like the repeated :106
+                        if (dt > 1e-280) dtt = dt * __longlong_as_double((long long)(1023 - lane) << 52);
+                        else for (int t = 0; t < lane; t++) dtt = dtt / 2;
                         bool done_t = true;                              // "this trial ends the :99 loop"
                         // trials exist while the previous one still had dt > time_tol; lane t >= 1 is a real trial iff
                         // dt_{t-1} > time_tol, which is monotone, so the first `done` lane below is always real
                         if (lane >= 1) {
                             // :99 only asks whether the largest overlap exceeds COLLISION_TOL: one pair above it decides
-                            // the trial, so the pair that was deepest in the check that just failed goes first
-                            int hm = 0;
-                            for (int h = 1; h < nh; h++)
-                                if (fabs(s.hmag[h]) > fabs(s.hmag[hm])) hm = h;
-                            int pfirst = 0;
-                            for (int p = 0; p < ns; p++)
-                                if (PM_II(s.sp[p]) == s.hi[hm] && PM_JJ(s.sp[p]) == s.hj[hm]) pfirst = p;
+                            // the trial
                             double mo = 0.0;
-                            for (int q = 0; q < ns && !(mo > kp.coll_tol); q++) {
-                                const int p = (q == 0) ? pfirst : (q <= pfirst ? q - 1 : q);
+                            for (int p = 0; p < ns && !(mo > kp.coll_tol); p++) {
                                 const pairmeta_t m = s.sp[p];
                                 const int ii = PM_II(m), jj = PM_JJ(m);
                                 double c1x, c1y, c2x = 0.0, c2y = 0.0;
