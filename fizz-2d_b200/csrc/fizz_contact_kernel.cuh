@@ -327,7 +327,6 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     const double vthr_r = __longlong_as_double(__double_as_longlong(kp.vib_thr) ^ opaque0);
     const double ope_r = __longlong_as_double(__double_as_longlong(kp.ope) ^ opaque0);
     const double hm_r = __longlong_as_double(__double_as_longlong(.5 * m1 * kp.ome2) ^ opaque0);
-    bool miss = false;
     double wnx = 0.0, wny = 0.0, nnvx = 0.0, nnvy = 0.0;  // check(): winning axis and the push it asks for
     bool okv = false;
     unsigned liveb = 0u;  // lanes of the slots whose pair collides, as of the last check()
@@ -394,12 +393,14 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
         const double dx = cpx - ox, dy = cpy - oy;
         const double d2 = fma(dy, dy, dx * dx);
-        surv = !(d2 > tmax);
+        const bool surv_l = !(d2 > tmax);
         // ---- memo check: edge k of b is (p2.y - p1.y, p1.x - p2.x) (:788-789) ----------------------------------------
+        // (surv_l / miss_l stay local: kept alive across the loop they would be computed twice per pass; the code after
+        //  the loop derives them again from the same registers)
         const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
-        miss = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
-                            ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
-        okv = __all_sync(FULL, !((surv != surv0) | miss) && one_live && mhi < 0x7ff00000u && passes < budget);
+        const bool miss_l = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
+                                         ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
+        okv = __all_sync(FULL, !((surv_l != surv0) | miss_l) && one_live && mhi < 0x7ff00000u && passes < budget);
         const double sc = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)) + eps_r;  // :158
         const bool m2_ = m1_ && low == mlo;
         const unsigned wl = __reduce_min_sync(FULL, m2_ ? (unsigned)lane : 32u);  // lowest axis index among equal minima
@@ -438,7 +439,18 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
             for (int v = 0; v < NM; v++) { vtx[v] += pnvx; vty[v] += pnvy; }         // :174
             ok = check(std::false_type{});
         }
-        if (!__any_sync(FULL, miss)) break;  // (with a stale memo the check above decided nothing: refresh, check again)
+        // (with a stale memo the check above decided nothing: refresh, check again)
+        {
+            const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
+            const bool miss_now = freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
+                                               (__double_as_longlong(ay) != __double_as_longlong(keyy)));
+            if (!__any_sync(FULL, miss_now)) break;
+        }
+    }
+    {   // the broad phase the last check() saw (same registers, same arithmetic)
+        const double dx = cpx - ox, dy = cpy - oy;
+        const double d2 = fma(dy, dy, dx * dx);
+        surv = !(d2 > tmax);
     }
     // The check that ended the loop, when it saw the same candidates and a separating axis for every one of them, IS the
     // check_collisions() of :234 that returns the empty list (pairs without b have not moved since the general path found
