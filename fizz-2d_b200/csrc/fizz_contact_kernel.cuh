@@ -111,6 +111,9 @@ __device__ __forceinline__ void edge_normal(const ContactSmem &s, int m, double 
 // One SAT axis of polypoly_collision (:787-830) for the packed pair `m` (ii free, jj free-or-fixed): axis index
 // k in [0, n1+n2) in reference order (poly1's edges, then poly2's), vertices read from the warp's explicit
 // vertex array.  Returns the overlap on this axis and whether the axis separates the polygons.
+// FLOOR = true: returns instead, in `cur`, min(hi2 - lo1, hi1 - lo2) of the intervals BEFORE the role swap of :815 -- a lower
+// bound of the overlap the axis reports whichever polygon ends up as "the first" (used by the trial-search shortcut).
+template <bool FLOOR = false>
 __device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, pairmeta_t m, int k, double &nx, double &ny,
                                          double &cur, bool &sep) {
     const int jj = PM_JJ(m), n1 = PM_N1(m), n2 = PM_N2(m), v1 = PM_V1(m), v2 = PM_V2(m);
@@ -157,6 +160,12 @@ __device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, pairmeta_t
                 if (c > hi2) hi2 = c;
             }
         }
+    }
+    if (FLOOR) {
+        const double a = hi2 - lo1, b = hi1 - lo2;
+        cur = (a < b) ? a : b;
+        sep = false;
+        return;
     }
     if (lo1 > lo2) {                                                         // :815-817
         double t = lo1; lo1 = lo2; lo2 = t;
@@ -742,10 +751,47 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         double dtt = dt;
                         if (dt > 1e-280) dtt = dt * __longlong_as_double((long long)(1023 - lane) << 52);
                         else for (int t = 0; t < lane; t++) dtt = dtt / 2;
+                        // Shortcut for a body that sits DEEP in a fixed one (the trapped pattern: every trial fails and the
+                        // loop ends on TIME_TOL): every trial position of that body lies within D of the position the
+                        // failed check saw -- pos(h) - pos(dt) = v (h - dt) + a0/2 (h^2 - dt^2), 0 < h <= dt -- and a
+                        // translation by d moves both ends of its projection on a unit axis by the same s, |s| <= |d|.
+                        // Whichever polygon :815 then calls "the first", the overlap the axis reports is one of
+                        // hi2 - lo1 - s and hi1 - lo2 + s, so min(hi2 - lo1, hi1 - lo2) - D bounds it from below.  If
+                        // that bound clears COLLISION_TOL (with a margin six orders above the rounding of the
+                        // projections) on every axis of the pair, the pair collides deeper than the tolerance in
+                        // every trial and no trial needs to be evaluated.  The broad phase is not an issue: all trials
+                        // of a timestep run on the survivors of the same stale snapshot (Q3).
+                        // (only in the latency-tuned instance: the first-chunk instance rarely sees deep contacts and pays for
+                        //  every instruction of footprint; and only when the reported overlap itself, an upper bound of the
+                        //  floor, clears the bar)
+                        bool all_fail = false;
+                        if constexpr (FAST) {
+                            int hm = -1;
+                            double best = kp.coll_tol;
+                            for (int h = 0; h < nh; h++)
+                                if (s.hj[h] >= F && fabs(s.hmag[h]) > best) { best = fabs(s.hmag[h]); hm = h; }
+                            if (hm >= 0) {  // (warp-uniform)
+                                const int ii = s.hi[hm], jj = s.hj[hm];
+                                const int na = kp.nv[ii] + kp.nv[jj];
+                                const pairmeta_t m = pack_pair(ii, jj, kp.nv[ii], kp.nv[jj], kp.vs[ii], kp.vs[jj]);
+                                double D = (fabs(s.vx[ii]) + fabs(s.vy[ii])) * dt + .5 * (fabs(a0x) + fabs(a0y)) * dt * dt;
+                                D = D * 1.000001 + 1e-9;
+                                bool clear = (best - D) > (kp.coll_tol + 1e-7);
+                                if (clear && lane < na) {
+                                    double fnx, fny, fl;
+                                    bool fsep;
+                                    sat_axis<true>(s, F, m, lane, fnx, fny, fl, fsep);
+                                    clear = (fl - D) > (kp.coll_tol + 1e-7 + 1e-9 * (fabs(fl) + D));  // (false for NaN)
+                                }
+                                all_fail = na <= 32 && __all_sync(FULL, clear);
+                            }
+                        }
                         bool done_t = true;                              // "this trial ends the :99 loop"
                         // trials exist while the previous one still had dt > time_tol; lane t >= 1 is a real trial iff
                         // dt_{t-1} > time_tol, which is monotone, so the first `done` lane below is always real
-                        if (lane >= 1) {
+                        if (lane >= 1 && all_fail) {
+                            done_t = !(dtt > kp.time_tol);
+                        } else if (lane >= 1) {
                             // :99 only asks whether the largest overlap exceeds COLLISION_TOL: one pair above it decides
                             // the trial
                             double mo = 0.0;
