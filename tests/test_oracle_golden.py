@@ -148,3 +148,28 @@ def test_oracle_ga_population():
         got, want = ow.contacts(), contact_rows(g[pre + "contacts_idx"], g[pre + "contacts_val"])
         assert [c[:4] for c in got] == [c[:4] for c in want], wi
         assert np.array_equal(bits([c[4:] for c in got]), bits([c[4:] for c in want])), wi
+
+
+@pytest.mark.parametrize("seed", [1003, 1007, 1012, 1018])
+def test_oracle_vs_live_reference_on_fuzz_scenes(seed):
+    """Where the unmodified reference can be imported (the build container), the C oracle is also checked against it
+    on scenes from the SAME random family the GPU fuzz test uses (tests/test_gpu_fuzz.py) -- polygons with up to 12
+    vertices, random PARAMs, gravity -- which the fixtures do not contain: every step, bit for bit."""
+    import sys
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness as rh
+    if not rh.available():
+        pytest.skip("/root/reference is not here")
+    from test_gpu_fuzz import random_scene
+    text, gravity = random_scene(seed)
+    ref = rh.RefWorld(text=text, max_calls=256, gravity=gravity if gravity != (0.0, 0.0) else None)
+    ow = orc.OracleWorld.from_text(text, gravity=gravity, max_calls=256)
+    for t in range(45):
+        alive = ref.update()
+        assert ow.update() == alive, (seed, t)
+        if not alive:
+            break
+        assert np.array_equal(bits(ow.com()), bits(ref.com())), (seed, t)
+        assert np.array_equal(bits(ow.verts()), bits(np.concatenate(ref.verts()))), (seed, t)
+        assert bits(ow.heat()) == bits(ref.heat()), (seed, t)
