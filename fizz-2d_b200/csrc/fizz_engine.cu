@@ -89,19 +89,26 @@ struct KernelInfo {
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process-wide: it must only ever grow, or a group
 // with a smaller footprint created later would make the launches of an earlier, larger group invalid.
+// (`current` is an array of MAX_DEVICES entries: the attribute belongs to the function ON A DEVICE, and one process may
+//  drive several)
+constexpr int MAX_DEVICES = 64;
 template <typename K>
 cudaError_t raise_dynamic_smem(K kernel, size_t smem, size_t *current) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t *cur = current + (dev >= 0 && dev < MAX_DEVICES ? dev : 0);
     const size_t want = smem > 48 * 1024 ? smem : 48 * 1024;
-    if (want <= *current) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    if (e == cudaSuccess) *current = want;
+    if (want <= *cur && dev < MAX_DEVICES) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e == cudaSuccess) *cur = want;
     return e;
 }
 
 template <int F>
 cudaError_t prep_thread(size_t smem, KernelInfo *ki) {
-    static size_t current = 0;
-    cudaError_t e = raise_dynamic_smem(step_kernel<F>, smem, &current);
+    static size_t current[MAX_DEVICES] = {};
+    cudaError_t e = raise_dynamic_smem(step_kernel<F>, smem, current);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&ki->attr, step_kernel<F>);
     if (e != cudaSuccess) return e;
@@ -109,8 +116,8 @@ cudaError_t prep_thread(size_t smem, KernelInfo *ki) {
 }
 template <int F>
 cudaError_t prep_ballistic(size_t smem, KernelInfo *ki, KernelInfo *kp_prover) {
-    static size_t current = 0;
-    cudaError_t e = raise_dynamic_smem(ballistic_kernel<F, true>, smem, &current);
+    static size_t current[MAX_DEVICES] = {};
+    cudaError_t e = raise_dynamic_smem(ballistic_kernel<F, true>, smem, current);
     if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&ki->attr, ballistic_kernel<F, false>);
     if (e != cudaSuccess) return e;
@@ -360,12 +367,12 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "ballistic kernel setup"); }
     g->contact_smem = contact_smem_bytes(kp.V, kp.FV);
     {
-        static size_t current_general = 0, current_trapped = 0;
-        e = raise_dynamic_smem(contact_kernel<false>, g->contact_smem, &current_general);
+        static size_t current_general[MAX_DEVICES] = {}, current_trapped[MAX_DEVICES] = {};
+        e = raise_dynamic_smem(contact_kernel<false>, g->contact_smem, current_general);
         // (runner launches ask for RUNNER_SMEM so that nothing else becomes resident on the SM that hosts them)
         if (e == cudaSuccess)
             e = raise_dynamic_smem(contact_kernel<true>, g->contact_smem > RUNNER_SMEM ? g->contact_smem : RUNNER_SMEM,
-                                   &current_trapped);
+                                   current_trapped);
     }
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&g->contact_ki.attr, contact_kernel<false>);
     if (e == cudaSuccess)
@@ -853,11 +860,8 @@ int fizz_raster_frames(int device, int32_t width, int32_t height, int64_t n_fram
     const size_t smem = 2 * sizeof(unsigned) * (size_t)height * rp.RW;
     if (smem > 227 * 1024) return fail(FIZZ_E_ARG, "fizz_raster_frames: frame too large for the shared memory of an SM");
     CU(cudaSetDevice(device));
-    static size_t raised = 0;
-    if (smem > 48 * 1024 && smem > raised) {
-        CU(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raised = smem;
-    }
+    static size_t raised[MAX_DEVICES] = {};
+    CU(raise_dynamic_smem(raster_kernel, smem, raised));
     raster_kernel<<<(unsigned)n_frames, RASTER_BLOCK, smem, (cudaStream_t)stream>>>(rp);
     CU(cudaGetLastError());
     return FIZZ_OK;
