@@ -1,11 +1,16 @@
 // fizz_engine.cu -- host side of the C-ABI (include/fizz_b200.h) + small utility kernels.
 //
-// Two execution modes per group (fizz_set_tuning):
+// Execution modes per group (fizz_set_tuning):
 //   FIZZ_MODE_HYBRID (default): per chunk of timesteps, (1) ballistic_kernel<F> -- thread per world, registers
 //     only, advances quiescent steps and stops a world at the first non-empty broad phase; (2) classify_kernel
 //     builds the list of worlds short of the chunk target; (3) contact_kernel -- persistent, warp per world,
 //     cooperative SAT / resolution -- brings those worlds to the chunk target.  No host synchronisation.
+//     Worlds found trapped and heavy leave this pipeline at a chunk boundary: "runner" launches of the contact kernel
+//     on library-owned streams step them to the end of the fizz_step() call (see fizz_step).
+//   FIZZ_MODE_HYBRID_SYNC: the same without runner launches.
+//   FIZZ_MODE_HYBRID3: adds the separation-prover tier and runs two contact-kernel instances side by side.
 //   FIZZ_MODE_THREAD: step_kernel<F> -- thread per world, full semantics in one launch.
+// Also here: the batched rasteriser's entry points (fizz_raster.cuh).
 #include "fizz_b200.h"
 
 #include "fizz_ballistic_kernel.cuh"
