@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--worlds", type=int, default=65536, help="worlds per GPU")
     ap.add_argument("--timesteps", type=int, default=10000)
-    ap.add_argument("--chunk", type=int, default=128, help="timesteps per chunk (hybrid mode)")
+    ap.add_argument("--chunk", type=int, default=96, help="timesteps per chunk (hybrid mode)")
     ap.add_argument("--mode", default="hybrid", choices=["hybrid", "hybrid_sync", "thread"])
     ap.add_argument("--max-calls", type=int, default=4096)
     ap.add_argument("--cpu-sample-worlds", type=int, default=16384)
