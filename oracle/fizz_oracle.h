@@ -3,7 +3,7 @@
  * A literal, scalar, one-world-at-a-time restatement in plain C of `World.update()` and its callees in
  * the reference (/root/reference/src/physics.py:66-289, :384-464, :502-529, :765-840).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.  The shipped
- * engine (fizz-2d_b200/csrc) never links or calls it.
+ * engine (fizz2d_b200/csrc) never links or calls it.
  *
  * Parity status: PINNED -- checked bit-for-bit against traces of the reference itself (run in the build
  * container through oracle/ref_harness.py) that are committed under tests/golden/.  The reference has no

@@ -4,7 +4,7 @@
   init-time math (`main.read_input` main.py:23-83, `Obj.__init__` physics.py:305-348, `Polygon.__init__`
   physics.py:610-644, `moment_of_inertia` :664-711, `triangle_area` :843-847,
   `triangle_moment_of_inertia` :849-868).  Written independently of the product loader
-  (`fizz-2d_b200/scene.py`) so the two can be checked against each other and against tests/golden/.
+  (`fizz2d_b200/scene.py`) so the two can be checked against each other and against tests/golden/.
 * `OracleWorld`: ctypes binding of `oracle/libfizz_oracle.so` (fizz_oracle.c), one world per object.
 
 Only tests/, `__graft_entry__.smoke()` and bench.py's cpu_baseline / `--impl reference` legs import this.

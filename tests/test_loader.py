@@ -1,4 +1,4 @@
-"""CPU: the product's host-side loader (fizz-2d_b200/scene.py, batch.GroupSpec) against the reference-derived
+"""CPU: the product's host-side loader (fizz2d_b200/scene.py, batch.GroupSpec) against the reference-derived
 fixtures and against the oracle's independent scalar restatement of the same init-time math."""
 import numpy as np
 import pytest
