@@ -234,18 +234,41 @@ class BatchedWorld:
             return torch.cuda.current_stream(self.device).cuda_stream
         return st.cuda_stream
 
-    def upload(self):
+    def _fork(self):
+        """Mixed batches step their groups concurrently on streams of their own: every group stream first waits for
+        what the caller's (torch's current) stream has queued so far ..."""
+        if self.streams[0] is not None:
+            import torch
+            cur = torch.cuda.current_stream(self.device)
+            for st in self.streams:
+                st.wait_stream(cur)
+
+    def _join(self):
+        """... and the caller's stream then waits for the group streams: from outside, a BatchedWorld call is ordered
+        on the current stream like any other torch operation (events recorded there bracket it)."""
+        if self.streams[0] is not None:
+            import torch
+            cur = torch.cuda.current_stream(self.device)
+            for st in self.streams:
+                cur.wait_stream(st)
+
+    def upload(self, sync=True):
         """(Re)load the initial conditions: host -> device, resets heat/status/step counters."""
+        self._fork()
         for k, g in enumerate(self.groups):
             g.upload(self._stream_ptr(k))
+        self._join()
         self.steps_requested = 0
-        self.synchronize()
+        if sync:
+            self.synchronize()
 
     def step(self, n_steps=1):
         """n_steps x World.update() for every world; one kernel launch per group (groups run concurrently)."""
         L = _lib.load()
+        self._fork()
         for k, g in enumerate(self.groups):
             _lib.check(L.fizz_step(g.handle, int(n_steps), C.c_void_p(self._stream_ptr(k))))
+        self._join()
         self.steps_requested += int(n_steps)
 
     def step_logged(self, n_steps):
@@ -254,10 +277,12 @@ class BatchedWorld:
         import torch
         L = _lib.load()
         logs = []
+        self._fork()
         for k, g in enumerate(self.groups):
             t = torch.empty((int(n_steps), 4, g.layout.stride), dtype=torch.float64, device=g.slab.device)
             _lib.check(L.fizz_step_logged(g.handle, int(n_steps), C.c_void_p(t.data_ptr()), C.c_void_p(self._stream_ptr(k))))
             logs.append(t)
+        self._join()
         self.steps_requested += int(n_steps)
         self.synchronize()
         out = np.empty((int(n_steps), self.n_worlds, 4))
@@ -298,7 +323,9 @@ class BatchedWorld:
         return bufs
 
     def download(self, **want):
+        self._fork()
         res = [self._download(g, k, **want) for k, g in enumerate(self.groups)]
+        self._join()
         self.synchronize()
         return res
 
@@ -390,22 +417,18 @@ class BatchedWorld:
         for gi in sorted(per_group):
             g = self.groups[gi]
             sp = g.spec
-            _lib.check(_lib.load().fizz_vertices(g.handle, C.c_void_p(self._stream_ptr(gi))))
-            if len(self.groups) > 1:
-                torch.cuda.synchronize(g.slab.device)    # groups step on their own streams, torch indexes on its own
+            # everything below (the library's kernels AND torch's indexing) runs on torch's current stream: one order
+            cur = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.load().fizz_vertices(g.handle, C.c_void_p(cur)))
             V = sum(sp.nverts_free)
             idx = torch.tensor(per_group[gi], dtype=torch.int64, device=g.slab.device)
             v = g.section("verts", 2 * V)[:, idx]                       # [2V, n]: rows x0, y0, x1, y1, ...
             verts = v.t().reshape(len(per_group[gi]), V, 2)              # [n, V, 2]
             fixed = np.array([(max(min(int(p[0]), sp.width - 1), 0), max(min(int(p[1]), sp.height - 1), 0))
                               for pts in sp.scene.fixed for p in pts], dtype=np.int32).reshape(-1, 2)
-            pts = raster.points_from_vertices(sp.width, sp.height, verts, fixed, device=g.device,
-                                              stream=self._stream_ptr(gi))
+            pts = raster.points_from_vertices(sp.width, sp.height, verts, fixed, device=g.device, stream=cur)
             nverts = list(sp.nverts_free) + [len(pts_) for pts_ in sp.scene.fixed]
-            outs.append(raster.render_points(sp.width, sp.height, nverts, pts, device=g.device,
-                                             stream=self._stream_ptr(gi)))
-        if len(self.groups) > 1:
-            torch.cuda.synchronize(self.groups[0].slab.device)
+            outs.append(raster.render_points(sp.width, sp.height, nverts, pts, device=g.device, stream=cur))
         return outs[0] if len(self.groups) == 1 else outs
 
     def locate(self, i):
@@ -443,17 +466,21 @@ class BatchedWorld:
         """Device-resident copy of the dynamic state of every group (replay without a host round trip)."""
         import torch
         snaps = []
+        self._fork()
         for k, g in enumerate(self.groups):
             t = torch.empty(g.layout.state_words, dtype=torch.float64, device=g.slab.device)
             _lib.check(_lib.load().fizz_snapshot(g.handle, C.c_void_p(t.data_ptr()), C.c_void_p(self._stream_ptr(k))))
             snaps.append(t)
+        self._join()
         return (snaps, self.steps_requested)
 
     def restore(self, snap):
         snaps, steps = snap
+        self._fork()
         for k, (g, t) in enumerate(zip(self.groups, snaps)):
             _lib.check(_lib.load().fizz_restore(g.handle, C.c_void_p(t.data_ptr()), int(steps),
                                                 C.c_void_p(self._stream_ptr(k))))
+        self._join()
         self.steps_requested = steps
 
     def set_profiling(self, enabled=True):

@@ -41,9 +41,13 @@ class World:
 
     def update(self, n=1):
         """World.update() (physics.py:76-259) for every world of the batch."""
-        if self.log is not None:                                                      # physics.py:81-82
-            self.log.write(','.join([str(x) for x in self.energy()]) + '\n')
-        self.batch.step(n)
+        if self.log is not None:
+            # one row BEFORE every update() (physics.py:81-82): n rows for n steps
+            rows = self.batch.step_logged(n)[:, self.view, :]
+            for r in rows:
+                self.log.write(','.join([str(x) for x in r]) + '\n')
+        else:
+            self.batch.step(n)
         for _ in range(n):
             self.state += self.time_disc                                              # physics.py:259
 

@@ -300,7 +300,7 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
 __global__ void live_kernel(const long long *status, const long long *steps, const long long *tier, long long W,
                             long long target, long long max_tier, long long *list, unsigned long long *count) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = (w < W) && status[w] == 0 && tier[w] <= max_tier && steps[w] > 0 && steps[w] < target;
+    const bool live = (w < W) && status[w] == 0 && (tier[w] & 255) <= max_tier && steps[w] > 0 && steps[w] < target;
     const unsigned b = __ballot_sync(0xffffffffu, live);
     if (b == 0) return;
     const int lane = threadIdx.x & 31;

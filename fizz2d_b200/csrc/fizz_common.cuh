@@ -33,6 +33,7 @@ struct KParams {
     long long trace_cap;
     long long W, Wp, target_steps;
     int F, X, V, FV;
+    int swl;                   // log2 of the narrow phase's slot width: 8, 16 or 32 lanes >= the largest n1 + n2 of the scene
     int nv[TAB], vs[TAB];      // vertices per body / first vertex (free: into the world's rows, fixed: into fixed_geom)
     double fcx[FIZZ_MAX_FIXED], fcy[FIZZ_MAX_FIXED], fthr[FIZZ_MAX_FIXED];
     double coll_tol, time_tol, eps, vib_tol, time_disc, ope, ome2, accx, accy;

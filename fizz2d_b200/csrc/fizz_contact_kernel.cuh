@@ -89,6 +89,12 @@ __device__ __forceinline__ ContactSmem contact_carve(double *base, int V, int FV
     return s;
 }
 
+// (ax, ay) / norm((ax, ay)) (:790): sqrt + two divisions, ~150 instructions with their slow paths -- ONE copy, out of line.
+__device__ __noinline__ double2 unit_normal(double ax, double ay) {
+    const double nrm = sqrt(fma(ay, ay, ax * ax));
+    return make_double2(ax / nrm, ay / nrm);
+}
+
 // Unit normal of the edge e -> e+1 of a free polygon whose vertices are (vx[e], vy[e]) (:775,:778,:790).
 // MEMO: read-write memo on the exact edge vector; pass false from code where several lanes may evaluate the same
 // edge with different vertex sets (speculative trials): then the memo is only read.
@@ -102,8 +108,8 @@ __device__ __forceinline__ void edge_normal(const ContactSmem &s, int m, double 
         __double_as_longlong(ay) == __double_as_longlong(s.may_[m])) {
         nx = s.mnx[m]; ny = s.mny[m];
     } else {
-        const double nrm = sqrt(fma(ay, ay, ax * ax));  // :790
-        nx = ax / nrm; ny = ay / nrm;
+        const double2 un = unit_normal(ax, ay);         // :790
+        nx = un.x; ny = un.y;
         if (MEMO_WRITE) { s.max_[m] = ax; s.may_[m] = ay; s.mnx[m] = nx; s.mny[m] = ny; }
     }
 }
@@ -239,27 +245,43 @@ __device__ __forceinline__ bool sat_pair_trial(const ContactSmem &s, int F, pair
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Single-contact resolve fast path.
+// Single-contact fast path: the resolve loop AND, while the pattern holds, whole timesteps, in registers.
 //
 // The worlds that bound a pass are a free polygon b trapped against FIXED polygons: every check_collisions() of
-// the resolve loop (:140-234) returns exactly one tuple (b, fixed j) for hundreds of passes per timestep.  Between
-// two such passes only b changes, so (1) every pair without b keeps its result ("no contact"), (2) only the pairs
-// (b, *) need the broad phase again, and as long as the same fixed partners (and no free body) pass it, (3) the
-// SAT work is a fixed set of (partner, axis) items.  This loop keeps b's vertices, the lane's axis constants, its
-// edge-normal memo and the partner's projection bounds in REGISTERS and runs check_collisions() + resolution
-// back to back; it returns to the general path -- with the state written back exactly as it is right before the
-// check_collisions() call at :234 -- as soon as anything else happens (other candidate set, zero or several
-// tuples, watchdog).  Arithmetic is the same, operation for operation, as the general path.
+// the resolve loop (:140-234) returns exactly one tuple (b, fixed j) for hundreds of passes per timestep, and the next
+// timestep starts the same way: trial 0 collides deeper than COLLISION_TOL (:99), every halving trial does too (proved,
+// not evaluated: see the contact kernel), the loop ends on TIME_TOL, the fallback (:133-137) reverts the centre of mass
+// and the resolve loop starts again.  Between two passes only b changes, so (1) every pair without b keeps its result
+// ("no contact"), (2) only the pairs (b, *) need the broad phase again, and as long as the same fixed partners (and no
+// free body) pass it, (3) the SAT work is a fixed set of (partner, axis) items.  trapped_run keeps b's vertices, the
+// lane's axis constants, its edge-normal memo and the partner's projection bounds in REGISTERS and runs
+// check_collisions() + resolution back to back; when the check that ends the resolve loop finds nothing it finishes
+// update() (:237-259) and starts the next one -- broad phase of all pairs on the snapshots, trial 0, the halving proof,
+// the last trial, the fallback -- without going back to the general path.  It returns
+//   TRAP_MIDSTEP   with the state written back exactly as it is right before the check_collisions() call at :234, as
+//                  soon as anything else happens inside a resolve loop (other candidate set, zero or several tuples,
+//                  watchdog): the general path continues that loop;
+//   TRAP_EMPTY     like TRAP_MIDSTEP, but the :234 check has been made (and counted) and found nothing: the general path
+//                  finishes update() (only for timesteps that did not take the fallback);
+//   TRAP_BOUNDARY  at a timestep boundary (target reached, or the next timestep does not start with the pattern: its
+//                  prologue is evaluated without side effects and discarded, the general path runs that timestep).
+// Arithmetic is the same, operation for operation, as the general path.
 // ---------------------------------------------------------------------------------------------------------------
-template <int N1>  // N1 = exact vertex count of b (3 or 4), or 0 = generic (<= 8 vertices, runtime count)
-__device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
-                                             double &heat, int &ncalls, long long &ncalls_total, bool &done_empty) {
-    constexpr int NM = N1 ? N1 : 8;
-    done_empty = false;
+enum { TRAP_MIDSTEP = 0, TRAP_EMPTY = 1, TRAP_BOUNDARY = 2 };
+
+// b has 3 or 4 vertices, kept in four register pairs: a triangle's first vertex (in the lane's rotation) sits there twice,
+// which changes neither a minimum nor a maximum of projections -- one instruction stream for both shapes (the kernel is
+// bound by instruction fetch wherever it is not bound by this chain).  MULTI = false: the variant of the throughput
+// instance, which leaves update()'s end and the next timestep to the general path (smaller footprint).
+template <bool MULTI>
+__device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
+                                           double &heat, int &ncalls, long long &ncalls_total, long long &step, int &k,
+                                           double &dt, int &steps_here, int &last_calls, const int kstar, const double dtk) {
+    constexpr int NM = 4;
     const unsigned FULL = 0xffffffffu;
-    const int n1 = N1 ? N1 : kp.nv[b];
+    const int n1 = kp.nv[b];
     const int v1 = kp.vs[b];
-    FIZZ_ASSERT(b >= 0 && b < F && n1 <= NM && (!N1 || kp.nv[b] == N1));
+    FIZZ_ASSERT(b >= 0 && b < F && (n1 == 3 || n1 == 4));
     double cpx = s.px[b], cpy = s.py[b], cvx = s.vx[b], cvy = s.vy[b];
     const double m1 = s.mass[b], thr_b = s.thr[b];
     // this lane's broad-phase partner: body `lane` of objs+fixed_objs.  (a-b)^2 == (b-a)^2 exactly, so the order of
@@ -278,9 +300,9 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     }
     const unsigned mask0 = __ballot_sync(FULL, surv);
     const int ncand = __popc(mask0);
-    if (ncand == 0 || ncand > 4 || (mask0 & ((1u << F) - 1u)) != 0) return;  // only fixed partners, one 32-lane set
+    if (ncand == 0 || ncand > 4 || (mask0 & ((1u << F) - 1u)) != 0) return TRAP_MIDSTEP;  // only fixed partners, one 32-lane set
 
-    const int slot = lane >> 3, k = lane & 7;
+    const int slot = lane >> 3, kk = lane & 7;
     int jj = -1;
     {
         unsigned mm = mask0;
@@ -289,20 +311,20 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     }
     int n2 = 0, v2 = 0;
     if (jj >= 0) { n2 = kp.nv[jj]; v2 = kp.vs[jj]; }
-    const bool active = (jj >= 0) && (k < n1 + n2);
-    const bool freeaxis = active && (k < n1);
+    const bool active = (jj >= 0) && (kk < n1 + n2);
+    const bool freeaxis = active && (kk < n1);
     const bool active_slot = (jj >= 0);
     const unsigned slot_bits = 0xffu << (8 * slot);
     // b's vertices, all of them in every lane, ROTATED so that a lane that owns edge k of b finds the edge's end points
     // in registers 0 and 1 (min/max over the same set of projections: only the sign of a zero could depend on order).
-    const int rot = freeaxis ? k : 0;
+    const int rot = freeaxis ? kk : 0;
     double vtx[NM], vty[NM];
 #pragma unroll
     for (int v = 0; v < NM; v++) {
         int src = rot + v;
-        if (src >= n1) src -= n1;
-        vtx[v] = (v < n1) ? s.vert[2 * (v1 + src)] : 0.0;
-        vty[v] = (v < n1) ? s.vert[2 * (v1 + src) + 1] : 0.0;
+        if (src >= n1) src -= n1;      // (v = 3 of a triangle: the vertex of v = 0 again)
+        vtx[v] = s.vert[2 * (v1 + src)];
+        vty[v] = s.vert[2 * (v1 + src) + 1];
     }
     // axis registers of this lane: unit normal, the partner's projection bounds on it and -- for an edge of b -- the
     // exact edge vector the normal was computed from (memo key; NaN = not computed yet).
@@ -312,11 +334,11 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     double anx = 0.0, any_ = 0.0, alo2 = active_slot ? -INFINITY : INFINITY, ahi2 = INFINITY;
     double keyx = NAN, keyy = NAN;  // (keys only used by edge lanes)
     if (active && !freeaxis) {
-        const double *g = s.sfix + (v2 + (k - n1)) * 6;
+        const double *g = s.sfix + (v2 + (kk - n1)) * 6;
         anx = g[2]; any_ = g[3]; alo2 = g[4]; ahi2 = g[5];
     }
     int passes = 0;
-    const int budget = kp.max_calls - ncalls;  // watchdog: the general path raises FIZZ_ST_CAPPED
+    int budget = kp.max_calls - ncalls;  // watchdog: the general path raises FIZZ_ST_CAPPED
     // (a "travel budget" that skips the broad phase while b cannot have reached a partner's threshold was measured and
     //  dropped: trapped bodies jump 20-100 px per pass, the budget is exhausted almost every pass)
     //
@@ -336,7 +358,9 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     const double vthr_r = __longlong_as_double(__double_as_longlong(kp.vib_thr) ^ opaque0);
     const double ope_r = __longlong_as_double(__double_as_longlong(kp.ope) ^ opaque0);
     const double hm_r = __longlong_as_double(__double_as_longlong(.5 * m1 * kp.ome2) ^ opaque0);
+    const double gate_min_r = __longlong_as_double(__double_as_longlong(2.0 * fabs(kp.vib_tol) + 1e-300) ^ opaque0);
     double wnx = 0.0, wny = 0.0, nnvx = 0.0, nnvy = 0.0;  // check(): winning axis and the push it asks for
+    double wmag = 0.0;                                    // ... and |overlap| on that axis
     bool okv = false;
     unsigned liveb = 0u;  // lanes of the slots whose pair collides, as of the last check()
 
@@ -345,27 +369,22 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
     //  velocity, heat, centre of mass, broad phase, memo check -- is issued while the warp-wide reductions are in flight)
     double pux = 0.0, puy = 0.0, pnvx = 0.0, pnvy = 0.0;  // previous pass: normal and push, for the deferred part
 
+    // b's projections on this lane's axis (:795-804)
+    auto project = [&](double &lo1, double &hi1) {
+        const double c0 = dot2(anx, any_, vtx[0], vty[0]), c1 = dot2(anx, any_, vtx[1], vty[1]);   // as a two-level tree
+        const double c2 = dot2(anx, any_, vtx[2], vty[2]), c3 = dot2(anx, any_, vtx[3], vty[3]);
+        const double la = (c1 < c0) ? c1 : c0, ha = (c1 > c0) ? c1 : c0;
+        const double lb = (c3 < c2) ? c3 : c2, hb = (c3 > c2) ? c3 : c2;
+        lo1 = (lb < la) ? lb : la;
+        hi1 = (hb > ha) ? hb : ha;
+    };
+
+    double plo1 = 0.0, phi1 = 0.0;   // b's projection bounds on this lane's axis as the last check(first) saw them
     auto check = [&](auto first) -> bool {
         // ---- narrow phase: one (partner, axis) item per lane --------------------------------------------------------
         double lo1, hi1;
-        if constexpr (N1 == 4) {                                                 // :795-804 as a two-level tree
-            const double c0 = dot2(anx, any_, vtx[0], vty[0]), c1 = dot2(anx, any_, vtx[1], vty[1]);
-            const double c2 = dot2(anx, any_, vtx[2], vty[2]), c3 = dot2(anx, any_, vtx[3], vty[3]);
-            const double la = (c1 < c0) ? c1 : c0, ha = (c1 > c0) ? c1 : c0;
-            const double lb = (c3 < c2) ? c3 : c2, hb = (c3 > c2) ? c3 : c2;
-            lo1 = (lb < la) ? lb : la;
-            hi1 = (hb > ha) ? hb : ha;
-        } else {
-            lo1 = hi1 = dot2(anx, any_, vtx[0], vty[0]);                         // :795
-#pragma unroll
-            for (int v = 1; v < NM; v++) {                                       // :799-804
-                if (N1 || v < n1) {
-                    const double c = dot2(anx, any_, vtx[v], vty[v]);
-                    if (c < lo1) lo1 = c;
-                    if (c > hi1) hi1 = c;
-                }
-            }
-        }
+        project(lo1, hi1);
+        if constexpr (decltype(first)::value) { plo1 = lo1; phi1 = hi1; }
         double lo2 = alo2, hi2 = ahi2;
         if (lo1 > lo2) {                                                         // :815-817
             double t = lo1; lo1 = lo2; lo2 = t;
@@ -387,7 +406,9 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         const unsigned mhi = __reduce_min_sync(FULL, mine ? hiw : 0xffffffffu);
         if constexpr (!decltype(first)::value) {
             // ---- rest of the previous resolution, free body vs fixed body (:180-198) ------------------------------
-            if (fma(pnvy, pnvy, pnvx * pnvx) > vthr_r) { cpx += pnvx; cpy += pnvy; }       // :180-181
+            // :180-181 norm(nv) > VIBRATE_TOL.  The latency-tuned variant only applies pushes that are certainly longer
+            // (see gate_min below): no test here
+            if (MULTI || fma(pnvy, pnvy, pnvx * pnvx) > vthr_r) { cpx += pnvx; cpy += pnvy; }
             const double vdotN = dot2(cvx, cvy, pux, puy);                           // :183
             const double cc = ope_r * vdotN;                                         // :188
             cvx -= cc * pux;
@@ -409,8 +430,12 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
         const bool miss_l = freeaxis & ((((unsigned long long)__double_as_longlong(ax) ^ (unsigned long long)__double_as_longlong(keyx)) |
                                          ((unsigned long long)__double_as_longlong(ay) ^ (unsigned long long)__double_as_longlong(keyy))) != 0ull);
-        okv = __all_sync(FULL, !((surv_l != surv0) | miss_l) && one_live && mhi < 0x7ff00000u && passes < budget);
-        const double sc = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo)) + eps_r;  // :158
+        wmag = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));   // fabs(overlap) (:125-129)
+        const double sc = wmag + eps_r;                                          // :158
+        // (MULTI: nv = -n (mag + EPSILON) with a unit normal n, so norm(nv) = (mag + EPSILON)(1 + O(1e-15)): twice the
+        //  tolerance settles the VIBRATE_TOL test of :180 without evaluating it; shorter pushes go to the general path)
+        const bool long_push = !MULTI || sc > gate_min_r;
+        okv = __all_sync(FULL, !((surv_l != surv0) | miss_l) && one_live && mhi < 0x7ff00000u && passes < budget && long_push);
         const bool m2_ = m1_ && low == mlo;
         const unsigned wl = __reduce_min_sync(FULL, m2_ ? (unsigned)lane : 32u);  // lowest axis index among equal minima
         wnx = __shfl_sync(FULL, anx, wl);                                        // the winning axis (:828-830)
@@ -420,27 +445,95 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
         return okv;
     };
 
-    for (;;) {
-        // ---- refresh the memo of the lanes whose edge vector changed: unit normal (:790), partner bounds (:806-811) -
-        {
-            const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
-            if (freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
-                             (__double_as_longlong(ay) != __double_as_longlong(keyy)))) {
-                const double nrm = sqrt(fma(ay, ay, ax * ax));
-                anx = ax / nrm; any_ = ay / nrm; keyx = ax; keyy = ay;
-                const double *g = s.sfix + v2 * 6;
-                alo2 = ahi2 = dot2(anx, any_, g[0], g[1]);
-                for (int v = 1; v < n2; v++) {
-                    const double c = dot2(anx, any_, g[v * 6], g[v * 6 + 1]);
-                    if (c < alo2) alo2 = c;
-                    if (c > ahi2) ahi2 = c;
-                }
+    // refresh the memo of the lanes whose edge vector changed: unit normal (:790), partner bounds (:806-811)
+    auto refresh = [&]() {
+        const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
+        if (freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
+                         (__double_as_longlong(ay) != __double_as_longlong(keyy)))) {
+            const double2 un = unit_normal(ax, ay);
+            anx = un.x; any_ = un.y; keyx = ax; keyy = ay;
+            const double *g = s.sfix + v2 * 6;
+            alo2 = ahi2 = dot2(anx, any_, g[0], g[1]);
+            for (int v = 1; v < n2; v++) {
+                const double c = dot2(anx, any_, g[v * 6], g[v * 6 + 1]);
+                if (c < alo2) alo2 = c;
+                if (c > ahi2) ahi2 = c;
             }
-            __syncwarp();
         }
+        __syncwarp();
+    };
+    auto memo_stale = [&]() -> bool {
+        const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
+        const bool miss_now = freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
+                                           (__double_as_longlong(ay) != __double_as_longlong(keyy)));
+        return __any_sync(FULL, miss_now);
+    };
+    // b's vertices as pre_update rebuilds them from a moved centre of mass (:358-359), in this lane's rotation
+    auto rebuild = [&](double cx, double cy) {
+#pragma unroll
+        for (int v = 0; v < NM; v++) {
+            int src = rot + v;
+            if (src >= n1) src -= n1;
+            vtx[v] = s.off[2 * (v1 + src)] + cx;
+            vty[v] = s.off[2 * (v1 + src) + 1] + cy;
+        }
+    };
+    const bool step_pattern_ok = kstar >= 1 && dtk < kp.time_tol && kp.time_disc > kp.time_tol;
+
+    // One copy of each check() in the instruction stream (the kernel is bound by instruction fetch wherever it is not
+    // bound by this chain): phase says what the check at the top of the outer loop is --
+    //   PH_RESOLVE  the :234 check of a resolve loop (entry from the general path, or again after a stale memo);
+    //   PH_TRIAL0   the first halving trial of a new timestep (:124), vertices rebuilt from the moved centre of mass;
+    //   PH_TRIALK   the last halving trial (and, same list, the fallback's check :137).
+    enum { PH_RESOLVE = 0, PH_TRIAL0 = 1, PH_TRIALK = 2 };
+    int phase = PH_RESOLVE;
+    bool in_prologue_step = false;   // the current timestep was started here: other bodies' trial vertices are not in smem
+    int ret = TRAP_BOUNDARY;
+    bool need_rebuild = false;       // the check at the top runs on vertices rebuilt from the centre of mass (rbx, rby)
+    double rbx = 0.0, rby = 0.0;
+    for (;;) {
+        if (need_rebuild) { rebuild(rbx, rby); need_rebuild = false; }
+        refresh();
         bool ok = check(std::true_type{});
+        if (MULTI && phase != PH_RESOLVE) {
+            // ======================= prologue of a new update() (:99-137), speculative =============================
+            // Nothing is stored anywhere but in this function's registers until the pattern is confirmed; if it is not,
+            // the general path runs this timestep from its start (ret = TRAP_BOUNDARY).
+            const double a0x = kp.accx, a0y = kp.accy;                      // step > 0 here
+            if (!ok) break;                                                 // not exactly one tuple (b, fixed)
+            if (phase == PH_TRIAL0) {
+                if (!(wmag > kp.coll_tol)) break;                           // :99 the halving loop would end here
+                // every halving trial fails (the contact kernel's proof, on this lane's axis of the colliding pair)
+                double D = (fabs(cvx) + fabs(cvy)) * kp.time_disc + .5 * (fabs(a0x) + fabs(a0y)) * kp.time_disc * kp.time_disc;
+                D = D * 1.000001 + 1e-9;
+                bool clear = (wmag - D) > (kp.coll_tol + 1e-7);
+                if (clear && active && (liveb & slot_bits) != 0u) {
+                    const double fa = ahi2 - plo1, fb = phi1 - alo2;
+                    const double fl = (fa < fb) ? fa : fb;
+                    clear = (fl - D) > (kp.coll_tol + 1e-7 + 1e-9 * (fabs(fl) + D));  // (false for NaN)
+                }
+                if (!__all_sync(FULL, clear)) break;
+                // trials 1 .. kstar-1 were made (and failed); trial kstar (:106-129)
+                double tvx_, tvy_;
+                FIZZ_MOVE_POINT(cpx, cpy, cvx, cvy, dtk, a0x, a0y, kp.accx, kp.accy, rbx, rby, tvx_, tvy_);
+                need_rebuild = true;
+                phase = PH_TRIALK;
+                continue;
+            }
+            // the fallback (:133-137): the centre of mass stays where the timestep started, the vertices keep the last
+            // trial's positions (Q5); its check returns the list of the last trial, whose resolve pass comes first and is
+            // not a call of its own (passes = -1)
+            k = kstar; dt = dtk;
+            ncalls = kstar + 2;                                             // trials 0 .. kstar and the fallback's check
+            ncalls_total += kstar + 2;
+            budget = kp.max_calls - ncalls;
+            passes = -1;
+            in_prologue_step = true;
+            phase = PH_RESOLVE;
+        }
+        // =============================== the resolve loop of the current timestep ================================
         while (ok) {
-            // ---- resolution, free body vs fixed body (:171-174); check() completes it (:180-198) ------------------
+            // ---- resolution, free body vs fixed body (:171-174); check() completes it (:180-198) --------------
             passes++;
             pux = wnx * -1.0; puy = wny * -1.0;                                      // :838-839
             pnvx = nnvx; pnvy = nnvy;
@@ -449,37 +542,122 @@ __device__ __forceinline__ void fast_resolve(const ContactSmem &s, const KParams
             ok = check(std::false_type{});
         }
         // (with a stale memo the check above decided nothing: refresh, check again)
-        {
-            const double ax = vty[1] - vty[0], ay = vtx[0] - vtx[1];
-            const bool miss_now = freeaxis && ((__double_as_longlong(ax) != __double_as_longlong(keyx)) ||
-                                               (__double_as_longlong(ay) != __double_as_longlong(keyy)));
-            if (!__any_sync(FULL, miss_now)) break;
+        if (memo_stale()) continue;
+        {   // the broad phase the last check() saw (same registers, same arithmetic)
+            const double dx = cpx - ox, dy = cpy - oy;
+            const double d2 = fma(dy, dy, dx * dx);
+            surv = !(d2 > tmax);
         }
+        // The check that ended the loop, when it saw the same candidates and a separating axis for every one of them, IS
+        // the check_collisions() of :234 that returns the empty list (pairs without b have not moved since the general
+        // path found them apart): count it and let update() finish, instead of having the general path find the same
+        // nothing again.
+        if (passes < 0) passes = 0;   // (the uncounted first pass was not even made: the watchdog or the memo came first)
+        const bool done_empty = !__any_sync(FULL, surv != surv0) && liveb == 0u && passes < budget;
+        if (done_empty) passes++;
+        ncalls += passes;
+        ncalls_total += passes;
+        passes = 0;
+        const bool fell_back = k > 0 && dt < kp.time_tol;
+        if (!MULTI || !done_empty || !fell_back || !step_pattern_ok) {
+            ret = done_empty ? TRAP_EMPTY : TRAP_MIDSTEP;
+            break;
+        }
+
+        // =============================== end of update() (:237-259), in registers ==================================
+        {
+            // :248-251 the rest of the timestep, no collision handling; the fallback reverted com.acc to the start-of-step
+            // acceleration (Q5), the move installs the world's
+            const bool acc_on = step > 0;
+            const double b0x = acc_on ? kp.accx : 0.0, b0y = acc_on ? kp.accy : 0.0;
+            const double rdt = kp.time_disc - dt;
+            double nx_, ny_, nvx_, nvy_;
+            FIZZ_MOVE_POINT(cpx, cpy, cvx, cvy, rdt, b0x, b0y, kp.accx, kp.accy, nx_, ny_, nvx_, nvy_);
+            cpx = nx_; cpy = ny_; cvx = nvx_; cvy = nvy_;
+            if (lane < F && lane != b) {
+                double ox_, oy_, ovx_, ovy_;
+                FIZZ_MOVE_POINT(s.px[lane], s.py[lane], s.vx[lane], s.vy[lane], rdt, b0x, b0y, kp.accx, kp.accy, ox_, oy_,
+                                ovx_, ovy_);
+                s.px[lane] = ox_; s.py[lane] = oy_; s.vx[lane] = ovx_; s.vy[lane] = ovy_;
+                s.sx[lane] = ox_; s.sy[lane] = oy_;                     // finish_update (:251)
+                ox = ox_; oy = oy_;                                     // this lane is b's broad-phase partner `lane`
+            }
+            if (lane == 0) {
+                s.px[b] = cpx; s.py[b] = cpy; s.vx[b] = cvx; s.vy[b] = cvy; s.sx[b] = cpx; s.sy[b] = cpy;
+            }
+            __syncwarp();
+            step++;                                                     // :259
+            steps_here++;
+            last_calls = ncalls;
+            k = 0; dt = kp.time_disc; ncalls = 0;                       // the state of a fresh update()
+            in_prologue_step = false;
+            ret = TRAP_BOUNDARY;
+        }
+        if (step >= kp.target_steps) break;
+        {
+            // broad phase of ALL pairs on the snapshots (:272-281): exactly the fixed partners of b, nothing else
+            unsigned pm = 0u;
+            bool other = false;
+            const int P = F * (F - 1) / 2 + F * X;
+            for (int p0 = 0; p0 < P; p0 += 32) {
+                const int p = p0 + lane;
+                if (p < P) {
+                    const pairmeta_t m = s.pair_meta[p];
+                    const int i = PM_II(m), j = PM_JJ(m);
+                    double qx, qy, qt;
+                    if (j < F) { qx = s.sx[j]; qy = s.sy[j]; qt = s.thr[j]; }
+                    else { qx = s.fcx[j - F]; qy = s.fcy[j - F]; qt = s.fthr[j - F]; }
+                    const double dx = s.sx[i] - qx, dy = s.sy[i] - qy;
+                    const double d2 = fma(dy, dy, dx * dx);
+                    if (!(d2 > s.thr[i] && d2 > qt)) {
+                        if (i == b && j >= F) pm |= 1u << j; else other = true;
+                    }
+                }
+            }
+            pm = __reduce_or_sync(FULL, pm);
+            if (__any_sync(FULL, other) || pm != mask0) break;
+        }
+        {
+            double tvx_, tvy_;                                          // trial 0 (:116-118)
+            FIZZ_MOVE_POINT(cpx, cpy, cvx, cvy, kp.time_disc, kp.accx, kp.accy, kp.accx, kp.accy, rbx, rby, tvx_, tvy_);
+            need_rebuild = true;
+        }
+        budget = 0x7fffffff;                                            // (the watchdog only counts in the resolve loop)
+        phase = PH_TRIAL0;
     }
-    {   // the broad phase the last check() saw (same registers, same arithmetic)
-        const double dx = cpx - ox, dy = cpy - oy;
-        const double d2 = fma(dy, dy, dx * dx);
-        surv = !(d2 > tmax);
-    }
-    // The check that ended the loop, when it saw the same candidates and a separating axis for every one of them, IS the
-    // check_collisions() of :234 that returns the empty list (pairs without b have not moved since the general path found
-    // them apart): count it and let update() finish, instead of having the general path find the same nothing again.
-    if (!__any_sync(FULL, surv != surv0) && liveb == 0u && passes < budget) {
-        passes++;
-        done_empty = true;
-    }
-    ncalls += passes;
-    ncalls_total += passes;
     // ---- write the state back for the general path ----------------------------------------------------------------
     __syncwarp();
-    if (lane < n1) { s.vert[2 * (v1 + lane)] = vtx[0]; s.vert[2 * (v1 + lane) + 1] = vty[0]; }  // slot 0, k = lane
     if (freeaxis && slot == 0 && keyx == keyx) {
-        s.max_[v1 + k] = keyx; s.may_[v1 + k] = keyy; s.mnx[v1 + k] = anx; s.mny[v1 + k] = any_;
+        s.max_[v1 + kk] = keyx; s.may_[v1 + kk] = keyy; s.mnx[v1 + kk] = anx; s.mny[v1 + kk] = any_;
     }
+    if (ret == TRAP_BOUNDARY) {
+        // a timestep boundary: b's state is in shared memory already, the vertices are derived state again
+        __syncwarp();
+        k = 0; dt = kp.time_disc; ncalls = 0;
+        return TRAP_BOUNDARY;
+    }
+    // inside a resolve loop, right before (TRAP_MIDSTEP) or after (TRAP_EMPTY) the check_collisions() call at :234
+    if (MULTI && in_prologue_step) {
+        // the timestep was started here: every OTHER body's vertices are where its last halving trial left them (Q5),
+        // |r|cos(phi) + com moved by dt_kstar (:358-359) -- the general path reads and stores them
+        const bool acc_on = step > 0;
+        const double a0x = acc_on ? kp.accx : 0.0, a0y = acc_on ? kp.accy : 0.0;
+        for (int v = lane; v < kp.V; v += 32) {
+            const int bb = s.vbody[v];
+            if (bb != b) {
+                double qx, qy, qvx, qvy;
+                FIZZ_MOVE_POINT(s.px[bb], s.py[bb], s.vx[bb], s.vy[bb], dt, a0x, a0y, kp.accx, kp.accy, qx, qy, qvx, qvy);
+                s.vert[2 * v] = s.off[2 * v] + qx;
+                s.vert[2 * v + 1] = s.off[2 * v + 1] + qy;
+            }
+        }
+    }
+    if (lane < n1) { s.vert[2 * (v1 + lane)] = vtx[0]; s.vert[2 * (v1 + lane) + 1] = vty[0]; }  // slot 0, k = lane
     if (lane == 0) {
         s.px[b] = cpx; s.py[b] = cpy; s.vx[b] = cvx; s.vy[b] = cvy; s.sx[b] = cpx; s.sy[b] = cpy;
     }
     __syncwarp();
+    return ret;
 }
 
 // Two instances of the same kernel, tuned for the two regimes of a batch:
@@ -499,7 +677,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(CONTACT_BLOCK, FAST ? FIZZ_FAST_CTAS : FIZZ_GEN_CTAS)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
                const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor,
-               unsigned long long count_cap = ~0ull) {
+               unsigned long long count_cap = ~0ull, int runner = 0) {
     extern __shared__ double smem_c[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -521,15 +699,25 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
     }
     __syncthreads();
 
-    // slot width of the narrow phase: smallest power of two >= the largest n1+n2 of the scene
-    int max_na = 0;
-    for (int i = 0; i < F; i++)
-        for (int j = i + 1; j < F + X; j++) max_na = max(max_na, kp.nv[i] + kp.nv[j]);
-    const int SW = max_na <= 8 ? 8 : (max_na <= 16 ? 16 : 32);
-    const int SWL = max_na <= 8 ? 3 : (max_na <= 16 ? 4 : 5);
+    // slot width of the narrow phase: smallest power of two >= the largest n1+n2 of the scene (host-computed)
+    const int SWL = kp.swl;
+    const int SW = 1 << SWL;
     const int PR = 32 >> SWL;                    // pairs per 32-lane set
     const int my_slot = lane >> SWL, my_k = lane & (SW - 1);
     const unsigned slot_mask = (SW == 32 ? FULL : ((1u << SW) - 1u)) << (my_slot * SW);
+
+    // The trial that ends the halving search of a timestep in which EVERY trial fails: dt / 2 / 2 ... (:106) is dt * 2^-t
+    // exactly as long as nothing gets subnormal; the first t >= 1 with dt_t <= TIME_TOL (:99).  (for trapped_run)
+    int kstar_all;
+    double dtk_all;
+    {
+        double dtt = kp.time_disc;
+        if (dtt > 1e-280) dtt = dtt * __longlong_as_double((long long)(1023 - lane) << 52);
+        else for (int t = 0; t < lane; t++) dtt = dtt / 2;
+        const unsigned doneb = __ballot_sync(FULL, lane >= 1 && !(dtt > kp.time_tol));
+        kstar_all = __ffs(doneb) - 1;
+        dtk_all = __shfl_sync(FULL, dtt, kstar_all < 0 ? 0 : kstar_all);
+    }
 
     const long long Wp = kp.Wp;
     const unsigned long long count = min(*count_ptr, count_cap);  // (a capped list: classify_kernel's `cap`)
@@ -557,6 +745,9 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
         double heat = kp.heat[w];
         long long step = kp.steps[w];
         const long long step_in = step;
+        // (a world that is at the target already -- listed by a reader that raced with another launch's write-back --
+        //  must not be touched: update() below runs before the target is tested)
+        if (step >= kp.target_steps) continue;
         long long status = 0;
         long long ncalls_total = 0, fast_calls = 0;
         __syncwarp();
@@ -564,6 +755,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
         bool resolve = false, verts_explicit = false;
         int k = 0, ncalls = 0, ns = 0;
         int fast_step = 0, calm = 0;  // tier-3 bookkeeping (scheduling hint only)
+        int last_calls = 0;           // check_collisions() of the last completed timestep, saturated (scheduling hint only)
         bool trapped = false;
         int quiet = 0;        // consecutive contact-free timesteps: one check_collisions(), no tuple (scheduling hint)
         int quiet_empty = 0;  // ... of those, consecutive ones whose broad phase was empty
@@ -895,18 +1087,32 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     __syncwarp();
                 }
                 resolve = true;  // next round: check_collisions() at :234
+#ifndef FIZZ_NO_TRAP
                 if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F) {
                     const int b = s.hi[0];
                     const long long before = ncalls_total;
                     const int nb = kp.nv[b];
-                    bool done_empty = false;
-                    if (nb == 4) fast_resolve<4>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, done_empty);
-                    else if (nb == 3) fast_resolve<3>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, done_empty);
-                    else if (nb <= 8) fast_resolve<0>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, done_empty);
+                    int ret = TRAP_MIDSTEP, steps_here = 0;
+                    // (one instantiation for triangles and quadrilaterals; anything else stays on the general path)
+                    if (nb == 3 || nb == 4)
+                        ret = trapped_run<FAST>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, step, k, dt, steps_here,
+                                                last_calls, kstar_all, dtk_all);
                     fast_calls += ncalls_total - before;
+                    if (steps_here) {
+                        // whole timesteps went by in registers: all of them trapped ones
+                        trapped = true; calm = 0; quiet = 0; quiet_empty = 0; fast_step = 0;
+                    }
+                    if (ret == TRAP_BOUNDARY) {
+                        // a fresh update() (or the target): the vertices are derived state again
+                        resolve = false; verts_explicit = false;
+                        if (step >= kp.target_steps) break;
+                        continue;
+                    }
+                    verts_explicit = true;
                     fast_step += (int)(ncalls_total - before);
-                    if (done_empty) goto end_of_update;  // the fast path made the :234 call that found nothing
+                    if (ret == TRAP_EMPTY) goto end_of_update;  // the fast path made the :234 call that found nothing
                 }
+#endif
                 continue;
             }
         end_of_update:
@@ -927,6 +1133,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             if (lane < F) { s.sx[lane] = s.px[lane]; s.sy[lane] = s.py[lane]; }  // finish_update (:237-239, :251)
             __syncwarp();
             step++;                                            // :259
+            last_calls = ncalls;
             quiet = (ncalls == 1) ? quiet + 1 : 0;  // (a step with a tuple makes at least two calls)
             quiet_empty = (ncalls == 1 && ns == 0) ? quiet_empty + 1 : 0;
             resolve = false; k = 0; dt = kp.time_disc; ncalls = 0;
@@ -967,7 +1174,13 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             // hint for the next chunk: 0 quiescent (lean thread-per-world kernel), 1 candidates but no contact (prover
             // variant, when enabled), 2 contact phase (stay here)
             const long long calm_tier = (quiet_empty >= 8) ? 0 : ((quiet >= 2) ? 1 : 2);
-            kp.tier[w] = FAST ? ((calm >= 8) ? calm_tier : 3) : (trapped ? 3 : calm_tier);
+            long long t = FAST ? ((calm >= 8) ? calm_tier : 3) : (trapped ? 3 : calm_tier);
+            // a runner launch never releases its worlds itself (tier 4 = "owned by a runner"): it runs on its own stream,
+            // and a work-list kernel of the chunk pipeline reading steps/tier while they are stored here could list a
+            // finished world again.  The host demotes tier 4 after the join at the end of fizz_step().
+            if (runner) t = 4;
+            // bits 8..31: check_collisions() of the last completed timestep: how heavy the world is NOW
+            kp.tier[w] = t | ((long long)(last_calls & 0xffffff) << 8);
             atomicAdd(kp.counters + 1, (unsigned long long)(step - step_in));
             atomicAdd(kp.counters + 2, (unsigned long long)ncalls_total);
             atomicAdd(kp.counters + 3, (unsigned long long)fast_calls);
@@ -977,19 +1190,26 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 }
 
 // Work list for the contact kernel: every running world that has not reached the chunk target.
-// `calls` / rate window: only worlds whose lifetime average of check_collisions() per timestep lies in [rate_lo,
-// rate_hi) are taken (pass calls = nullptr to take all): lets the host append the heaviest worlds first.
+// The tier word holds the scheduling hint in bits 0..7 and the check_collisions() count of the world's last completed
+// timestep in bits 8..31.  `use_rate`: only worlds whose last timestep made [rate_lo, rate_hi) calls
+// are taken: lets the host append the heaviest worlds first.
 // `mark` >= 0: the selected worlds get tier = mark (runner mode: 4 = "owned by a runner launch", which keeps every other
-// kernel of the pipeline away from them until the runner has stored them again).
+// kernel of the pipeline away from them until the host releases them after the join).
 __global__ void classify_kernel(const long long *status, const long long *steps, long long *tier, long long W,
-                                long long target, long long tier_lo, long long tier_hi, const long long *calls,
+                                long long target, long long tier_lo, long long tier_hi, int use_rate,
                                 long long rate_lo, long long rate_hi, long long *list, unsigned long long *count,
                                 long long mark = -1, unsigned long long cap = ~0ull) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool lag = (w < W) && status[w] == 0 && steps[w] < target && tier[w] >= tier_lo && tier[w] <= tier_hi;
-    if (lag && calls) {
-        const long long c = calls[w], n = steps[w] > 0 ? steps[w] : 1;
-        lag = c >= rate_lo * n && c < rate_hi * n;
+    long long tw = 0;
+    bool lag = false;
+    if (w < W) {
+        tw = tier[w];                                  // (tier before steps: see the write-back of the contact kernel)
+        const long long t = tw & 255;
+        lag = status[w] == 0 && t >= tier_lo && t <= tier_hi && steps[w] < target;
+    }
+    if (lag && use_rate) {
+        const long long r = (tw >> 8) & 0xffffff;
+        lag = r >= rate_lo && r < rate_hi;
     }
     const unsigned b = __ballot_sync(0xffffffffu, lag);
     if (b == 0) return;
@@ -1000,8 +1220,15 @@ __global__ void classify_kernel(const long long *status, const long long *steps,
     const unsigned long long idx = base + __popc(b & ((1u << lane) - 1u));
     if (lag && idx < cap) {       // (beyond `cap` a world is neither listed nor marked: the count is clamped by the reader)
         list[idx] = w;
-        if (mark >= 0) tier[w] = mark;
+        if (mark >= 0) tier[w] = (tw & ~255LL) | mark;
     }
+}
+
+// End of a fizz_step() call, after the join with the runner launches: their worlds go back to the chunk pipeline as
+// "trapped" (tier 3).
+__global__ void release_kernel(long long *tier, long long W) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < W && (tier[w] & 255) == 4) tier[w] = (tier[w] & ~255LL) | 3;
 }
 
 // Derived vertices for worlds whose point.pos are not explicit state: |r|cos(phi) + com.x, |r|sin(phi) + com.y

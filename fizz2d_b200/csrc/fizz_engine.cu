@@ -19,6 +19,7 @@
 #include "fizz_raster.cuh"
 #include "fizz_thread_kernel.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -119,19 +120,26 @@ cudaError_t prep_thread(size_t smem, KernelInfo *ki) {
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, step_kernel<F>, BLOCK, smem);
 }
+// The lean variant must work; the prover variant (FIZZ_MODE_HYBRID3 only) needs shared memory that a vertex-rich scene
+// may not leave: then only that mode is unavailable (*prover_ok = false), the group is still created.
 template <int F>
-cudaError_t prep_ballistic(size_t smem, KernelInfo *ki, KernelInfo *kp_prover) {
+cudaError_t prep_ballistic(size_t smem, KernelInfo *ki, KernelInfo *kp_prover, bool *prover_ok) {
     static size_t current[MAX_DEVICES] = {};
-    cudaError_t e = raise_dynamic_smem(ballistic_kernel<F, true>, smem, current);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&ki->attr, ballistic_kernel<F, false>);
+    cudaError_t e = cudaFuncGetAttributes(&ki->attr, ballistic_kernel<F, false>);
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, ballistic_kernel<F, false>, BALLISTIC_BLOCK, 0);
     if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&kp_prover->attr, ballistic_kernel<F, true>);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kp_prover->blocks_per_sm, ballistic_kernel<F, true>,
-                                                         BALLISTIC_BLOCK, smem);
+    *prover_ok = false;
+    std::memset(kp_prover, 0, sizeof(*kp_prover));
+    if (raise_dynamic_smem(ballistic_kernel<F, true>, smem, current) == cudaSuccess &&
+        cudaFuncGetAttributes(&kp_prover->attr, ballistic_kernel<F, true>) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kp_prover->blocks_per_sm, ballistic_kernel<F, true>, BALLISTIC_BLOCK,
+                                                      smem) == cudaSuccess &&
+        kp_prover->blocks_per_sm >= 1)
+        *prover_ok = true;
+    else
+        (void)cudaGetLastError();
+    return cudaSuccess;
 }
 
 #define FIZZ_DISPATCH_F(F_, CALL)          \
@@ -169,6 +177,7 @@ struct FizzGroup {
     size_t thread_smem;
     KernelInfo thread_ki;
     bool thread_ok;
+    bool prover_ok;   // ballistic_kernel<F, true> fits (FIZZ_MODE_HYBRID3)
     // hybrid mode
     KernelInfo ballistic_ki, prover_ki, contact_ki, trapped_ki;
     size_t contact_smem, ballistic_smem;
@@ -193,16 +202,21 @@ struct FizzGroup {
     std::vector<ProfSpan> spans;
     double prof_ms[3];   // accumulated: thread, ballistic, classify+contact
     long long prof_launches[3];
+    cudaError_t prof_error;  // first failure of a timing event (fizz_step reports it)
 };
 
+// Next timing event of the pool, recorded on `st`; nullptr (and the error latched for fizz_step to report) when the
+// runtime refuses to create or record one.
 static cudaEvent_t next_event(FizzGroup *g, cudaStream_t st) {
     if (g->ev_used == g->ev_pool.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = nullptr;
+        const cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) { g->prof_error = rc; return nullptr; }
         g->ev_pool.push_back(e);
     }
     cudaEvent_t e = g->ev_pool[g->ev_used++];
-    cudaEventRecord(e, st);
+    const cudaError_t rc = cudaEventRecord(e, st);
+    if (rc != cudaSuccess) { g->prof_error = rc; return nullptr; }
     return e;
 }
 
@@ -295,7 +309,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     g->sm_count = prop.multiProcessorCount;
     g->uploaded = false; g->target = 0; g->launches = 0;
     g->mode = FIZZ_MODE_HYBRID; g->chunk = 256;
-    g->profile = false; g->ev_used = 0;
+    g->profile = false; g->ev_used = 0; g->prof_error = cudaSuccess;
     g->side = nullptr; g->ev_fork = nullptr; g->ev_join = nullptr;
     g->rlist = nullptr; g->rcount = nullptr;
     for (int i = 0; i < FizzGroup::NR; i++) { g->rstream[i] = nullptr; g->rdone[i] = nullptr; }
@@ -321,6 +335,12 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
         else { kp.vs[b] = vfix; vfix += d->nverts[b]; }
     }
     kp.FV = vfix;
+    {
+        int max_na = 0;
+        for (int i = 0; i < F; i++)
+            for (int j = i + 1; j < F + X; j++) max_na = std::max(max_na, kp.nv[i] + kp.nv[j]);
+        kp.swl = max_na <= 8 ? 3 : (max_na <= 16 ? 4 : 5);
+    }
     double *fixed_dev = s + L.scene;
     kp.fixed_geom = fixed_dev;
     g->vbody_dev = (unsigned char *)(fixed_dev + round_up((long long)vfix * 6, 16));
@@ -368,7 +388,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     if (!g->thread_ok) (void)cudaGetLastError();
     // hybrid mode
     g->ballistic_smem = ballistic_smem_bytes(F, kp.V, kp.FV);
-    FIZZ_DISPATCH_F(F, e = prep_ballistic<FF>(g->ballistic_smem, &g->ballistic_ki, &g->prover_ki));
+    FIZZ_DISPATCH_F(F, e = prep_ballistic<FF>(g->ballistic_smem, &g->ballistic_ki, &g->prover_ki, &g->prover_ok));
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "ballistic kernel setup"); }
     g->contact_smem = contact_smem_bytes(kp.V, kp.FV);
     {
@@ -387,9 +407,11 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->trapped_ki.blocks_per_sm, contact_kernel<true>, CONTACT_BLOCK,
                                                           g->contact_smem);
-    if (e != cudaSuccess || g->contact_ki.blocks_per_sm < 1 || g->trapped_ki.blocks_per_sm < 1) {
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "contact kernel setup"); }
+    if (g->contact_ki.blocks_per_sm < 1 || g->trapped_ki.blocks_per_sm < 1) {
         delete g;
-        return cuda_fail(e, "contact kernel setup");
+        return fail(FIZZ_E_ARG, "fizz_group_create: the scene does not fit in the shared memory of an SM (contact kernel: "
+                                "too many free/fixed vertices)");
     }
     e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
@@ -453,6 +475,8 @@ int fizz_set_tuning(FizzGroup *g, int32_t mode, int64_t chunk_steps) {
         return fail(FIZZ_E_ARG, "fizz_set_tuning: unknown mode");
     if (mode == FIZZ_MODE_THREAD && !g->thread_ok)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: thread mode does not fit in shared memory for this topology");
+    if (mode == FIZZ_MODE_HYBRID3 && !g->prover_ok)
+        return fail(FIZZ_E_ARG, "fizz_set_tuning: hybrid3 mode: the prover tier does not fit in shared memory for this topology");
     if (chunk_steps < 1) return fail(FIZZ_E_ARG, "fizz_set_tuning: chunk_steps must be >= 1");
     g->mode = mode;
     g->chunk = chunk_steps;
@@ -525,7 +549,11 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         dim3 grid((unsigned)(g->lay.stride / BLOCK));
         cudaEvent_t ea = g->profile ? next_event(g, st) : nullptr;
         FIZZ_DISPATCH_F(F, (step_kernel<FF><<<grid, BLOCK, g->thread_smem, st>>>(kp)));
-        if (g->profile) g->spans.push_back({FIZZ_KERNEL_THREAD, ea, next_event(g, st)});
+        if (g->profile) {
+            cudaEvent_t eb = next_event(g, st);
+            if (ea && eb) g->spans.push_back({FIZZ_KERNEL_THREAD, ea, eb});
+            if (g->prof_error != cudaSuccess) return cuda_fail(g->prof_error, "fizz_step: timing event");
+        }
         CU(cudaGetLastError());
         g->launches++;
         return FIZZ_OK;
@@ -544,7 +572,8 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     // before the join below, and a runner waits for nothing.  Short calls (per-timestep stepping) do not bother.
     const long long final_target = g->target + n_steps;
 #ifdef FIZZ_RUNNER_DEBUG
-    cudaEvent_t d0 = nullptr;
+    cudaEvent_t d0 = nullptr, d_chunk[64] = {};
+    long long d_len[64] = {};
     cudaEventCreate(&d0);
     cudaEventRecord(d0, st);
 #endif
@@ -553,7 +582,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     int rnext = 0;
     const unsigned long long runner_cap = (unsigned long long)g->rcap;  // all resident at once, see FizzGroup::rcap
     const dim3 rgrid((unsigned)(kneed < g->sm_count ? kneed : g->sm_count));
-    const long long runner_rate = 48;   // check_collisions() per timestep, lifetime average
+    const long long runner_rate = 48;   // check_collisions() in the world's last completed timestep
     const size_t runner_smem = g->contact_smem > RUNNER_SMEM ? g->contact_smem : RUNNER_SMEM;
     int64_t nchunk = 0;
     for (int64_t done = 0; done < n_steps; nchunk++) {
@@ -589,22 +618,22 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                 unsigned long long *rc = g->rcount + 2 * slot;
                 long long *rl = g->rlist + (size_t)slot * (size_t)g->rcap;
                 CU(cudaMemsetAsync(rc, 0, 2 * sizeof(unsigned long long), st));
-                // candidates: flagged trapped AND heavy over their lifetime (>= 48 check_collisions() per timestep: the
+                // candidates: flagged trapped AND heavy right now (>= 48 check_collisions() in their last timestep: the
                 // heaviest ~0.3 % of config 3) -- half of all worlds see one long resolve loop early on, and a runner
                 // list longer than the grid would make the worlds at its end wait instead of run (hence also the cap).
                 // A runner CTA asks for RUNNER_SMEM of shared memory, i.e. for an SM of its own: measured on config 3,
                 // sharing SMs with the chunk pipeline makes the longest chain 0-20 % slower depending on where it lands
                 // (540-640 ms per pass), alone it is 545-560 ms every time (no runners: 580-620)
                 // (two passes so that the very heaviest get their slots first when the cap bites)
-                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, kp.calls,
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, 1,
                                                        3 * runner_rate, 1LL << 40, rl, rc, 4, runner_cap);
-                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, kp.calls,
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, 1,
                                                        runner_rate, 3 * runner_rate, rl, rc, 4, runner_cap);
                 CU(cudaEventRecord(g->ev_fork, st));
                 CU(cudaStreamWaitEvent(g->rstream[slot], g->ev_fork, 0));
                 KParams kr = kp;
                 kr.target_steps = final_target;
-                contact_kernel<true><<<rgrid, CONTACT_BLOCK, runner_smem, g->rstream[slot]>>>(kr, rl, rc, rc + 1, runner_cap);
+                contact_kernel<true><<<rgrid, CONTACT_BLOCK, runner_smem, g->rstream[slot]>>>(kr, rl, rc, rc + 1, runner_cap, 1);
                 rused[slot] = true;
                 g->launches += 2;
             }
@@ -612,7 +641,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             // world with the longest chain of resolve passes never waits for anything
             // (work list in world order: measured -- grouping the trapped worlds at the head of the list, or sorting them
             //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, nullptr, 0, 1,
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
                                                    g->sched_list, g->sched_count);   // (tier 4: owned by a runner)
             // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
             // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
@@ -628,9 +657,9 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             // 3 at the start of the chunk) on the library's side stream, the compact high-occupancy general instance
             // (everything else that lags) on the caller's stream.  Both bring their worlds to the chunk target; the
             // general instance only FLAGS the worlds it finds trapped, the hand-over happens at the next chunk.
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 3, 3, nullptr, 0, 1, g->sched_list2,
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 3, 3, 0, 0, 1, g->sched_list2,
                                                    g->sched_count + 2);
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 2, nullptr, 0, 1, g->sched_list,
+            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 2, 0, 0, 1, g->sched_list,
                                                    g->sched_count);
             CU(cudaEventRecord(g->ev_fork, st));
             CU(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
@@ -642,12 +671,17 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             CU(cudaStreamWaitEvent(st, g->ev_join, 0));
         }
         if (g->profile) {
-            g->spans.push_back({FIZZ_KERNEL_BALLISTIC, ea, eb});
-            g->spans.push_back({FIZZ_KERNEL_CONTACT, eb, next_event(g, st)});
+            cudaEvent_t ec = next_event(g, st);
+            if (ea && eb) g->spans.push_back({FIZZ_KERNEL_BALLISTIC, ea, eb});
+            if (eb && ec) g->spans.push_back({FIZZ_KERNEL_CONTACT, eb, ec});
+            if (g->prof_error != cudaSuccess) return cuda_fail(g->prof_error, "fizz_step: timing event");
         }
         CU(cudaGetLastError());
         g->launches += 6;
         done += c;
+#ifdef FIZZ_RUNNER_DEBUG
+        if (nchunk < 64) { cudaEventCreate(&d_chunk[nchunk]); cudaEventRecord(d_chunk[nchunk], st); d_len[nchunk] = c; }
+#endif
     }
     bool any = false;
 #ifdef FIZZ_RUNNER_DEBUG
@@ -664,9 +698,11 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             any = true;
         }
     if (any) {
-        // whatever is still short of the target (a world flagged trapped by the last chunks, when no stream was idle)
+        // the runners' worlds go back to the pipeline (the only place tier 4 is released: see the contact kernel)
+        release_kernel<<<cgrid, 256, 0, st>>>(kp.tier, W);
+        // whatever is still short of the target (a world beyond a runner list's cap)
         CU(cudaMemsetAsync(g->sched_count, 0, 2 * sizeof(unsigned long long), st));
-        classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 0, 4, nullptr, 0, 1,
+        classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 0, 4, 0, 0, 1,
                                                g->sched_list, g->sched_count);
         kp.target_steps = final_target;
         contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
@@ -684,6 +720,9 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             if (d_run[i]) { cudaEventElapsedTime(&t, d0, d_run[i]); fprintf(stderr, " runner%d %.1f", i, t); cudaEventDestroy(d_run[i]); }
         unsigned long long rc[2 * FizzGroup::NR];
         cudaMemcpy(rc, g->rcount, sizeof(rc), cudaMemcpyDeviceToHost);
+        fprintf(stderr, " | chunks (len@ms):");
+        for (int i = 0; i < 64; i++)
+            if (d_chunk[i]) { cudaEventElapsedTime(&t, d0, d_chunk[i]); fprintf(stderr, " %lld@%.1f", d_len[i], t); cudaEventDestroy(d_chunk[i]); }
         fprintf(stderr, " | list sizes:");
         for (int i = 0; i < FizzGroup::NR; i++) fprintf(stderr, " %llu", rc[2 * i]);
         fprintf(stderr, "\n");

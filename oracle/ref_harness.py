@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- harness that imports the UNMODIFIED reference (read-only at
 /root/reference) through a small shim and records full-precision traces of `World.update()`.
 
-It exists to (1) pin the C restatement in `oracle/fizz_oracle.c` and (2) generate the golden fixtures
-committed under `tests/golden/` (see `oracle/make_golden.py`).  It can only run where `/root/reference`
-exists (the build container); nothing in `-m gpu` tests, `smoke()` or `bench.py` imports it.
+It exists to (1) pin the C restatement in `oracle/fizz_oracle.c`, (2) generate the golden fixtures
+committed under `tests/golden/` (see `oracle/make_golden.py`) and (3) time the reference itself as bench.py's CPU
+baseline (`oracle/cpu_arm.py`).  It runs where `/root/reference` exists (the build container) or, on the GPU box,
+from the verbatim copy `make -C oracle ref` leaves under the git-ignored `oracle/_ref/pyref/`; no `-m gpu` test and
+no smoke() imports it.
 
 Shim (no reference file is edited or copied):
   * `matplotlib` is stubbed (main.py:19 -> plot.py:1 imports it; absent here),
@@ -31,6 +33,10 @@ import numpy as np
 REF_ROOT = os.environ.get("FIZZ_REFERENCE_ROOT", "/root/reference")
 REF_SRC = os.path.join(REF_ROOT, "src")
 SCENES = os.path.join(REF_ROOT, "simulations")
+if not os.path.isfile(os.path.join(REF_SRC, "physics.py")):
+    # the GPU box has no /root/reference: `make -C oracle ref` left a verbatim copy of the reference's Python sources
+    # under oracle/_ref/pyref/ (git-ignored, travels with the gpurun snapshot) for bench.py's CPU-baseline leg
+    REF_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")
 
 # line numbers of the check_collisions() call sites inside World.update (physics.py)
 _SITE_TRIAL, _SITE_FALLBACK, _SITE_RESOLVE = 124, 137, 234

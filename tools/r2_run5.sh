@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest5.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest5.log
+timeout 300 python tools/heavy_probe.py 63739,12860 10000 2>&1 | tail -2
+echo "=== new lib timeline"; FIZZ_B200_LIB=$PWD/tmp_variants/libfizz_dbg.so timeout 300 python tools/timeline_probe.py 96 2>&1 | tail -2
+timeout 300 python tools/first_chunk.py 96 > gpurun_out/fc_plain.log 2>&1 && cat gpurun_out/fc_plain.log && timeout 900 ncu --set full --clock-control none --import-source on -k regex:contact_kernel -s 1 -c 1 -f -o gpurun_out/r02_chunk1b python tools/first_chunk.py 96 > gpurun_out/ncu_fc.log 2>&1; echo "ncu rc=$?"

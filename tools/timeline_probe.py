@@ -1,0 +1,15 @@
+"""One pass of the benchmark batch with a FIZZ_RUNNER_DEBUG build of the library (FIZZ_B200_LIB=...): when every chunk
+boundary is reached, when each runner launch ends, how long the runner lists are."""
+import sys, time
+import torch
+sys.path.insert(0, ".")
+import fizz2d_b200 as fz
+chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+mode = sys.argv[2] if len(sys.argv) > 2 else "hybrid"
+bw = fz.BatchedWorld.from_in(fz.scenes.scene_path("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=65536, perturb=True, seed=20260003)
+bw.set_tuning(mode, chunk)
+snap = bw.snapshot()
+for rep in range(3):
+    bw.restore(snap); torch.cuda.synchronize()
+    t0 = time.perf_counter(); bw.step(10000); torch.cuda.synchronize()
+    print("pass %d: %.1f ms" % (rep, (time.perf_counter() - t0) * 1e3), flush=True)
