@@ -359,15 +359,15 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
     const double ope_r = __longlong_as_double(__double_as_longlong(kp.ope) ^ opaque0);
     const double hm_r = __longlong_as_double(__double_as_longlong(.5 * m1 * kp.ome2) ^ opaque0);
     const double gate_min_r = __longlong_as_double(__double_as_longlong(2.0 * fabs(kp.vib_tol) + 1e-300) ^ opaque0);
-    double wnx = 0.0, wny = 0.0, nnvx = 0.0, nnvy = 0.0;  // check(): winning axis and the push it asks for
-    double wmag = 0.0;                                    // ... and |overlap| on that axis
+    double wmag = 0.0;                                    // check(): |overlap| on the winning axis
     bool okv = false;
     unsigned liveb = 0u;  // lanes of the slots whose pair collides, as of the last check()
 
     // (the latency of one warp is also why the statements below are ordered the way they are: the chain
     //  push -> vertices -> projections -> ballot -> three redux -> shuffle comes first, and the rest of a pass --
     //  velocity, heat, centre of mass, broad phase, memo check -- is issued while the warp-wide reductions are in flight)
-    double pux = 0.0, puy = 0.0, pnvx = 0.0, pnvy = 0.0;  // previous pass: normal and push, for the deferred part
+    // check() leaves the negated winning axis and the push it asks for here; the next check() completes that resolution
+    double pux = 0.0, puy = 0.0, pnvx = 0.0, pnvy = 0.0;
 
     // b's projections on this lane's axis (:795-804)
     auto project = [&](double &lo1, double &hi1) {
@@ -438,10 +438,12 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
         okv = __all_sync(FULL, !((surv_l != surv0) | miss_l) && one_live && mhi < 0x7ff00000u && passes < budget && long_push);
         const bool m2_ = m1_ && low == mlo;
         const unsigned wl = __reduce_min_sync(FULL, m2_ ? (unsigned)lane : 32u);  // lowest axis index among equal minima
-        wnx = __shfl_sync(FULL, anx, wl);                                        // the winning axis (:828-830)
-        wny = __shfl_sync(FULL, any_, wl);
-        nnvx = (wnx * -1.0) * sc;                                                // :838-839, :158
-        nnvy = (wny * -1.0) * sc;
+        // the winning axis (:828-830), negated (:838-839), and the push it asks for (:158): straight into the registers the
+        // NEXT check's deferred part reads (their old values were consumed above; copies at the back edge cost issue slots)
+        pux = __shfl_sync(FULL, anx, wl) * -1.0;
+        puy = __shfl_sync(FULL, any_, wl) * -1.0;
+        pnvx = pux * sc;
+        pnvy = puy * sc;
         return okv;
     };
 
@@ -535,8 +537,6 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
         while (ok) {
             // ---- resolution, free body vs fixed body (:171-174); check() completes it (:180-198) --------------
             passes++;
-            pux = wnx * -1.0; puy = wny * -1.0;                                      // :838-839
-            pnvx = nnvx; pnvy = nnvy;
 #pragma unroll
             for (int v = 0; v < NM; v++) { vtx[v] += pnvx; vty[v] += pnvy; }         // :174
             ok = check(std::false_type{});
