@@ -9,10 +9,24 @@ ARGV[4] PNG (spawn ./draw like the reference, main.py:101-116), ARGV[5] energy l
 off-by-one of the reference.  The extra flags run N perturbed copies of the scene in lockstep on the
 GPU and print world `--view`; without them the run is the reference run.
 """
+import os
 import subprocess
 import sys
 
 from . import compat
+
+
+def _draw(start, end, wait):
+    """./draw START END (main.py:106,111) when the reference's rasteriser has been built next to us, else the same frames
+    from the GPU rasteriser (fizz2d_b200.raster, pixel-identical to draw.c)."""
+    if os.path.isfile("./draw") and os.access("./draw", os.X_OK):
+        if wait:
+            subprocess.run(["./draw", str(start), str(end)])
+            return None
+        return subprocess.Popen(["./draw", str(start), str(end), "&"])
+    from . import raster
+    raster.main([str(start), str(end)])
+    return None
 
 
 def main(argv=None):
@@ -40,9 +54,11 @@ def main(argv=None):
         with open(compat.SIMULATION_DIR + "plane_%03d.txt" % t, "w") as f:
             f.write(str(plane))
         if png and t and t % 126 == 0:
-            processes.append(subprocess.Popen(["./draw", str(t - 126), str(t), "&"]))
+            p = _draw(t - 126, t, wait=False)
+            if p is not None:
+                processes.append(p)
     if png:
-        subprocess.run(["./draw", str(t - (t % 126)), str(t)])
+        _draw(t - (t % 126), t, wait=True)
         for p in processes:
             p.wait()
     if energylog:

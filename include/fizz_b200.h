@@ -104,7 +104,8 @@ typedef struct FizzLayout {
     int64_t steps;      /* [1]   int64 completed update() calls                        */
     int64_t calls;      /* [1]   int64 state-relevant check_collisions() calls, lifetime */
     int64_t vflag;      /* [1]   int64 1 = `verts` holds explicit point.pos (pushed by a resolve pass), 0 = derived */
-    int64_t tier;       /* [1]   int64 scheduling hint: 0 quiescent, 1 candidates/no contact, 2 contact phase, 3 trapped */
+    int64_t tier;       /* [1]   int64 scheduling hint, bits 0..7: 0 quiescent, 1 candidates/no contact, 2 contact phase,
+                                 3 trapped, 4 owned by a runner launch; bits 8..31: check_collisions() of the last step */
     int64_t state_words;/* words from `pos` to the end of `tier` */
     /* per-world constants */
     int64_t off;        /* [V*2] |r|cos(phi), |r|sin(phi) per free vertex (physics.py:358-359,632-635) */
@@ -163,7 +164,13 @@ int fizz_upload(FizzGroup *g, const double *pos, const double *vel, const double
  * launch and one persistent contact launch (warp per world).  Thread mode: one launch for all n_steps.
  * FIZZ_MODE_HYBRID, n_steps >= 128: worlds found trapped are additionally handed to "runner" launches on streams the
  * library owns; each of them is forked from `stream` by an event and joined back into `stream` before the call
- * returns, so whatever the caller enqueues on `stream` afterwards sees every world at its target. */
+ * returns, so whatever the caller enqueues on `stream` afterwards sees every world at its target.
+ *
+ * STREAM CONTRACT.  A group is stepped, uploaded, restored and read on ONE stream at a time: the library-owned runner
+ * streams, runner work lists and events of a group are reused by the next fizz_step() call on the strength of the
+ * previous call's join INTO ITS `stream`.  Consecutive calls for one group must therefore be issued on the same stream,
+ * or on streams the caller has ordered with an event (the second call's stream waits for the first call's work);
+ * calls for DIFFERENT groups may run on different streams concurrently.  The calls are not thread-safe per group. */
 int fizz_step(FizzGroup *g, int64_t n_steps, void *stream);
 
 /* Streaming variant: like fizz_step, but before every timestep t the World.energy() row of EVERY world

@@ -191,8 +191,19 @@ def gen_anchors():
         json.dump(out, f, indent=1)
 
 
+def gen_critical():
+    """The benchmark regime itself: the two worlds with the longest chains of BASELINE config 3 -- a square
+    trapped inside a fixed rectangle from timestep 83 / 6 on, ~330 / ~275 check_collisions() per timestep, every resolve
+    pass one tuple -- with the benchmark's watchdog (max_calls = 4096), through the reference itself."""
+    d = fz.perturbation_deltas(20260003, 65536, 7)
+    gen_perturbed("critical_rampworld", lambda w: "RAMPWORLD_2TRIANGLES_5SQUARES", d, [12860, 63739], 130, [60, 100, 130], 4096)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--critical" in sys.argv:
+        gen_critical()
+        return
     for name in SCENES:
         gen_scene(name, 320)
     # gravity extension (reachable only through the Python API in the reference, SURVEY section 0)
@@ -212,6 +223,7 @@ def main():
     gen_perturbed("config4_mixed", lambda w: "2CHAMBERS_3BALLS" if w % 2 == 0 else "STACKEDCHAMBERS_1SQUARE", d,
                   list(range(1, 13)), 300, [100, 200, 300], 256)
     gen_ga("config5_pentagonvoid", "PENTAGONVOID_1SQUARE", 20260005, list(range(0, 24)), 300, [100, 200, 300], 256)
+    gen_critical()
     gen_anchors()
 
 

@@ -89,7 +89,8 @@ def test_1000_step_anchors_through_text_formats(name):
 @pytest.mark.parametrize("mode", MODES, ids=["hybrid256", "hybrid3-7", "thread"])
 @pytest.mark.parametrize("tag,seed,nw,fmax", [("config2_boxfriction", 20260002, 4096, 1),
                                              ("config3_rampworld", 20260003, 65536, 7),
-                                             ("config4_mixed", 20260004, 262144, 3)])
+                                             ("config4_mixed", 20260004, 262144, 3),
+                                             ("critical_rampworld", 20260003, 65536, 7)])
 def test_perturbed_worlds_match_reference(tag, seed, nw, fmax, mode):
     """Worlds of the BASELINE configs (same seeds, same law) that the reference itself was run on, including
     worlds the watchdog caps."""
@@ -127,6 +128,33 @@ def test_perturbed_worlds_match_reference(tag, seed, nw, fmax, mode):
             want = contact_rows(g[pre + "contacts_idx"], g[pre + "contacts_val"])
             assert [c[:4] for c in got] == [c[:4] for c in want], (scene, k)
             assert np.array_equal(bits([c[4:] for c in got]), bits([c[4:] for c in want]))
+
+
+@pytest.mark.parametrize("mode", [("hybrid", 256), ("hybrid", 16), ("hybrid3", 32), ("hybrid_sync", 64)],
+                         ids=["hybrid256", "hybrid16", "hybrid3-32", "hybrid_sync64"])
+def test_critical_worlds_match_reference_without_trace(mode):
+    """The benchmark regime against the REFERENCE ITSELF (fixture perturbed_critical_rampworld: the two longest chains of
+    BASELINE config 3, max_calls = 4096, 130 timesteps, ~330 check_collisions() per timestep once trapped), with the
+    contact trace OFF: the speculative halving search, its all-trials-fail proof and the register-resident trapped path
+    are what runs here -- state, vertices, heat and the per-world call total must still be the reference's bits."""
+    g = golden("perturbed_critical_rampworld")
+    sc = fz.parse_in(str(golden("RAMPWORLD_2TRIANGLES_5SQUARES")["scene_text"]))
+    d = np.ascontiguousarray(g["deltas"][:, :sc.n_free, :])
+    bw = tune(fz.BatchedWorld([GroupSpec.from_scene(sc, len(d), d, max_calls=int(g["max_calls"]))]), mode)
+    done = 0
+    for c in [int(c) for c in g["checkpoints"]]:
+        bw.step(c - done)
+        done = c
+        com = bw.com()
+        for k, wi in enumerate(g["worlds"]):
+            assert np.array_equal(bits(com[k]), bits(g["w%d_com_at_%d" % (int(wi), c)])), (wi, c)
+    com, verts, heat, calls, k4 = bw.com(), bw.vertices(), bw.heat(), bw.calls(), bw.counters()[0]
+    assert k4["fast_path_calls"] > 0.7 * k4["contact_calls"]
+    for k, wi in enumerate(g["worlds"]):
+        pre = "w%d_" % int(wi)
+        assert np.array_equal(bits(com[k]), bits(g[pre + "final_com"])) and bits(heat[k]) == bits(g[pre + "final_heat"])
+        assert np.array_equal(bits(verts[k]), bits(g[pre + "final_verts"]))
+        assert calls[k] == int(g[pre + "calls"].sum()), wi
 
 
 @pytest.mark.parametrize("mode", [("hybrid", 50), ("hybrid3", 32), ("thread", 1)], ids=["hybrid50", "hybrid3-32", "thread"])

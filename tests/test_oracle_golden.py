@@ -73,7 +73,7 @@ def test_oracle_1000_step_anchors(name):
     assert np.array_equal(bits(ow.com()), bits(anchors["final_com"]))
 
 
-@pytest.mark.parametrize("tag", ["config2_boxfriction", "config3_rampworld", "config4_mixed"])
+@pytest.mark.parametrize("tag", ["config2_boxfriction", "config3_rampworld", "config4_mixed", "critical_rampworld"])
 def test_oracle_perturbed_worlds(tag):
     """Perturbed worlds (SURVEY 8d law), including worlds the watchdog caps: final state, checkpoints, per-step
     call counts and the full contact trace equal the reference's."""
