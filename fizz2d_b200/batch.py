@@ -20,8 +20,10 @@ class GroupSpec:
     """Host-side description of one group: topology + fixed geometry + per-world SoA initial conditions."""
 
     def __init__(self, scene: _scene.Scene, points: Sequence[np.ndarray], velocity: np.ndarray,
-                 density: np.ndarray, gravity=(0.0, 0.0), max_calls=4096, check_valid=True):
-        """points[b]: (W, n_b, 2) vertices of free body b per world; velocity: (W, F, 2); density: (W, F)."""
+                 density: np.ndarray, gravity=(0.0, 0.0), max_calls=4096, check_valid=True, friction=None,
+                 ff_restitution=None):
+        """points[b]: (W, n_b, 2) vertices of free body b per world; velocity: (W, F, 2); density: (W, F).
+        friction / ff_restitution: the default-off physics extensions (see scene.resolve_params)."""
         self.scene = scene
         self.width, self.height = scene.width, scene.height
         F = len(points)
@@ -64,7 +66,7 @@ class GroupSpec:
             self.fixed_com[j] = c["com"][0]
             self.fixed_radius[j] = c["radius"][0]
         self.fixed_thr = _scene.sqrt_threshold(self.fixed_radius)
-        self.params = _scene.resolve_params(scene.params, gravity, scene.height, max_calls)
+        self.params = _scene.resolve_params(scene.params, gravity, scene.height, max_calls, friction, ff_restitution)
 
     @classmethod
     def from_scene(cls, scene: _scene.Scene, n_worlds=1, deltas: Optional[np.ndarray] = None, **kw):
@@ -171,15 +173,18 @@ class BatchedWorld:
     # -- construction ------------------------------------------------------------------------------------
     @classmethod
     def from_in(cls, path, n_worlds=1, perturb=False, seed=0, dpos=5.0, dvel=30.0, gravity=(0.0, 0.0),
-                max_calls=4096, device=0):
+                max_calls=4096, device=0, friction=None, ff_restitution=None):
         sc = _scene.load_in(path)
         deltas = _scene.perturbation_deltas(seed, n_worlds, sc.n_free, dpos, dvel) if perturb else None
-        return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls)], device=device)
+        return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls, friction=friction,
+                                         ff_restitution=ff_restitution)], device=device)
 
     @classmethod
-    def from_text(cls, text, n_worlds=1, deltas=None, gravity=(0.0, 0.0), max_calls=4096, device=0):
+    def from_text(cls, text, n_worlds=1, deltas=None, gravity=(0.0, 0.0), max_calls=4096, device=0, friction=None,
+                  ff_restitution=None):
         sc = _scene.parse_in(text)
-        return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls)], device=device)
+        return cls([GroupSpec.from_scene(sc, n_worlds, deltas, gravity=gravity, max_calls=max_calls, friction=friction,
+                                         ff_restitution=ff_restitution)], device=device)
 
     @classmethod
     def from_mixed(cls, paths, n_worlds, seed=0, perturb=True, dpos=5.0, dvel=30.0, max_calls=4096, device=0):

@@ -37,6 +37,7 @@ struct KParams {
     int nv[TAB], vs[TAB];      // vertices per body / first vertex (free: into the world's rows, fixed: into fixed_geom)
     double fcx[FIZZ_MAX_FIXED], fcy[FIZZ_MAX_FIXED], fthr[FIZZ_MAX_FIXED];
     double coll_tol, time_tol, eps, vib_tol, time_disc, ope, ome2, accx, accy;
+    double mu, ffr;            // extensions (fizz_ext.cuh): Coulomb coefficient (0 = off), free-free restitution (< 0 = off)
     double vib_thr;            // T(vib_tol): norm(nv) > VIBRATE_TOL  <=>  fma(nvy,nvy,nvx*nvx) > vib_thr  (:180)
     int max_calls;
 };

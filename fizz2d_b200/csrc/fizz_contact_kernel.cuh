@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "fizz_common.cuh"
+#include "fizz_ext.cuh"
 
 namespace fizz {
 
@@ -1054,6 +1055,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         cvx -= cc * ux;
                         cvy -= cc * uy;
                         heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                    // :191,:195
+                        if (kp.mu > 0.0) ext_friction_fixed(kp.mu, kp.ope, m1, ux, uy, vdotN, cvx, cvy, heat);  // (extension)
                         __syncwarp();
                         if (lane == 0) {
                             s.px[ii] = cpx; s.py[ii] = cpy; s.vx[ii] = cvx; s.vy[ii] = cvy;
@@ -1069,13 +1071,17 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         double c2x = s.px[jj], c2y = s.py[jj], v2x = s.vx[jj], v2y = s.vy[jj];
                         const double vn1 = dot2(v1x, v1y, ux, uy);                      // :207
                         const double vn2 = dot2(v2x, v2y, ux, uy);                      // :208
-                        const double v1u = (mprop1 - mprop2) * vn1 + 2 * mprop2 * vn2;  // :209
-                        const double v2u = 2 * mprop1 * vn1 + (mprop2 - mprop1) * vn2;  // :218
+                        double v1u = (mprop1 - mprop2) * vn1 + 2 * mprop2 * vn2;        // :209
+                        double v2u = 2 * mprop1 * vn1 + (mprop2 - mprop1) * vn2;        // :218
+                        if (kp.ffr >= 0.0) ext_restitution_free(kp.ffr, m1, mprop1, mprop2, vn1, vn2, v1u, v2u, heat);  // (extension)
                         const double d1 = v1u - vn1, d2 = v2u - vn2;                    // :210,:219
                         const double p1x = mprop1 * nvx, p1y = mprop1 * nvy;
                         const double p2x = mprop2 * nvx, p2y = mprop2 * nvy;
                         c1x += p1x; c1y += p1y; v1x += d1 * ux; v1y += d1 * uy;         // :206,:210
                         c2x -= p2x; c2y -= p2y; v2x += d2 * ux; v2y += d2 * uy;         // :217,:219
+                        if (kp.mu > 0.0)                                                // (extension)
+                            ext_friction_free(kp.mu, kp.ffr >= 0.0 ? kp.ffr : 1.0, m1, m2, mprop2, ux, uy, vn1, vn2, v1x, v1y,
+                                              v2x, v2y, heat);
                         if (lane < n1) { s.vert[2 * (v1 + lane)] += p1x; s.vert[2 * (v1 + lane) + 1] += p1y; }  // :212
                         if (lane < n2) { s.vert[2 * (v2 + lane)] -= p2x; s.vert[2 * (v2 + lane) + 1] -= p2y; }  // :221
                         __syncwarp();
@@ -1088,7 +1094,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 }
                 resolve = true;  // next round: check_collisions() at :234
 #ifndef FIZZ_NO_TRAP
-                if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F) {
+                if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F && !(kp.mu > 0.0)) {   // (friction: general path only)
                     const int b = s.hi[0];
                     const long long before = ncalls_total;
                     const int nb = kp.nv[b];

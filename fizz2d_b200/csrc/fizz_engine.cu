@@ -296,6 +296,8 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     if (rc) return rc;
     if (!dev_slab || slab_words < L.total_words) return fail(FIZZ_E_ARG, "fizz_group_create: slab too small");
     if (d->params.max_calls < 32) return fail(FIZZ_E_ARG, "fizz_group_create: max_calls must be >= 32");
+    if (!(d->params.friction_mu >= 0.0)) return fail(FIZZ_E_ARG, "fizz_group_create: friction_mu must be >= 0 (0 = off)");
+    if (!(d->params.ff_restitution <= 1.0)) return fail(FIZZ_E_ARG, "fizz_group_create: ff_restitution must be <= 1 (< 0 = off)");
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(FIZZ_E_CUDA, "fizz_group_create: no such CUDA device");
@@ -379,6 +381,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     kp.coll_tol = p.collision_tol; kp.time_tol = p.time_tol; kp.eps = p.epsilon; kp.vib_tol = p.vibrate_tol;
     kp.time_disc = p.time_disc; kp.ope = p.one_plus_e; kp.ome2 = p.one_minus_e2; kp.accx = p.acc_x; kp.accy = p.acc_y;
     kp.max_calls = p.max_calls;
+    kp.mu = p.friction_mu; kp.ffr = p.ff_restitution;
     fizz_host_sqrt_threshold(1, &p.vibrate_tol, &kp.vib_thr);
 
     // thread mode (may not fit in shared memory for vertex-rich worlds: then only hybrid mode is available)

@@ -10,6 +10,7 @@
 #pragma once
 
 #include "fizz_common.cuh"
+#include "fizz_ext.cuh"
 
 namespace fizz {
 
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
                             vx[b] -= cc * ux;
                             vy[b] -= cc * uy;
                             heat += .5 * m1 * kp.ome2 * (vdotN * vdotN);                         // :191,:195
+                            if (kp.mu > 0.0) ext_friction_fixed(kp.mu, kp.ope, m1, ux, uy, vdotN, vx[b], vy[b], heat);
                             sx[b] = px[b]; sy[b] = py[b];                                        // :197
                         }
                     }
@@ -312,21 +314,27 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
                     }
                     const double vn1 = dot2(v1x, v1y, ux, uy);                                   // :207
                     const double vn2 = dot2(v2x, v2y, ux, uy);                                   // :208
-                    const double v1u = (mprop1 - mprop2) * vn1 + 2 * mprop2 * vn2;               // :209
-                    const double v2u = 2 * mprop1 * vn1 + (mprop2 - mprop1) * vn2;               // :218
+                    double v1u = (mprop1 - mprop2) * vn1 + 2 * mprop2 * vn2;                     // :209
+                    double v2u = 2 * mprop1 * vn1 + (mprop2 - mprop1) * vn2;                     // :218
+                    if (kp.ffr >= 0.0) ext_restitution_free(kp.ffr, m1, mprop1, mprop2, vn1, vn2, v1u, v2u, heat);
                     const double d1 = v1u - vn1, d2 = v2u - vn2;                                 // :210,:219
+                    v1x += d1 * ux; v1y += d1 * uy;                                              // :210
+                    v2x += d2 * ux; v2y += d2 * uy;                                              // :219
+                    if (kp.mu > 0.0)
+                        ext_friction_free(kp.mu, kp.ffr >= 0.0 ? kp.ffr : 1.0, m1, m2, mprop2, ux, uy, vn1, vn2, v1x, v1y, v2x,
+                                          v2y, heat);
                     const double p1x = mprop1 * nvx, p1y = mprop1 * nvy;
                     const double p2x = mprop2 * nvx, p2y = mprop2 * nvy;
 #pragma unroll
                     for (int b = 0; b < F; b++) {
                         if (b == ii) {
                             px[b] += p1x; py[b] += p1y;                                          // :206
-                            vx[b] += d1 * ux; vy[b] += d1 * uy;                                  // :210
+                            vx[b] = v1x; vy[b] = v1y;
                             sx[b] = px[b]; sy[b] = py[b];                                        // :215
                         }
                         if (b == jj) {
                             px[b] -= p2x; py[b] -= p2y;                                          // :217
-                            vx[b] += d2 * ux; vy[b] += d2 * uy;                                  // :219
+                            vx[b] = v2x; vy[b] = v2y;
                             sx[b] = px[b]; sy[b] = py[b];                                        // :223
                         }
                     }

@@ -23,7 +23,8 @@ lp = C.POINTER(C.c_int64)
 class FizzParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "elasticity", "epsilon", "time_tol", "collision_tol", "vibrate_tol", "time_disc", "gx", "gy",
-        "one_plus_e", "one_minus_e2", "acc_x", "acc_y", "height")] + [("max_calls", C.c_int32), ("reserved", C.c_int32)]
+        "one_plus_e", "one_minus_e2", "acc_x", "acc_y", "height", "friction_mu", "ff_restitution")] + \
+        [("max_calls", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FizzGroupDesc(C.Structure):
@@ -95,7 +96,7 @@ def load():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.fizz_abi_version() != 1:
+        if L.fizz_abi_version() != 2:
             raise FizzError("ABI version mismatch")
         _lib = L
     return _lib

@@ -24,6 +24,8 @@ TIME_DISC = .05
 # names `PARAM` may set that the hot path reads at call time; others have no effect there
 _LIVE_PARAMS = set(DEFAULT_PARAMS)
 _INERT_PARAMS = {"TIME_DISC", "GRAVITY", "GLOBALROTSPEED", "DENSITY", "CONTACT_TOL", "ANGLE_TOL"}
+# default-off extensions of this engine (csrc/fizz_ext.cuh); the reference's parser would setattr() them without effect
+_EXT_PARAMS = {"FRICTION", "FF_RESTITUTION"}
 
 
 @dataclasses.dataclass
@@ -76,7 +78,7 @@ def parse_in(text: str, name: str = "") -> Scene:
         words = line.split()
         if words[0] == "PARAM":
             name_, val = words[1], float(words[2])
-            if name_ not in _LIVE_PARAMS:
+            if name_ not in _LIVE_PARAMS and name_ not in _EXT_PARAMS:
                 if name_ in _INERT_PARAMS:
                     warnings.warn("PARAM %s has no effect on the stepping path (bound at definition time in the "
                                   "reference, physics.py:32-33)" % name_)
@@ -227,13 +229,21 @@ def perturbation_deltas(seed: int, n_worlds: int, n_free: int, dpos: float = 5.0
     return d
 
 
-def resolve_params(scene_params: dict, gravity=(0.0, 0.0), height=0, max_calls=4096):
-    """FizzParams with the derived fields evaluated as the Python float expressions of the reference."""
+def resolve_params(scene_params: dict, gravity=(0.0, 0.0), height=0, max_calls=4096, friction=None, ff_restitution=None):
+    """FizzParams with the derived fields evaluated as the Python float expressions of the reference.
+    friction / ff_restitution: the default-off extensions (Coulomb coefficient; restitution between two free bodies);
+    None = what the scene's `PARAM FRICTION` / `PARAM FF_RESTITUTION` lines say, else off."""
     p = dict(DEFAULT_PARAMS)
     p.update({k: v for k, v in scene_params.items() if k in _LIVE_PARAMS})
     e = p["ELASTICITY"]
     gx, gy = float(gravity[0]), float(gravity[1])
-    return _lib.FizzParams(
+    mu = float(scene_params.get("FRICTION", 0.0) if friction is None else friction)
+    ffr = float(scene_params.get("FF_RESTITUTION", -1.0) if ff_restitution is None else ff_restitution)
+    if not mu >= 0.0:
+        raise ValueError("friction must be >= 0")
+    if ffr > 1.0:
+        raise ValueError("ff_restitution must be in [0, 1] (or negative: off)")
+    return _lib.FizzParams(friction_mu=mu, ff_restitution=ffr, 
         elasticity=e, epsilon=p["EPSILON"], time_tol=p["TIME_TOL"], collision_tol=p["COLLISION_TOL"],
         vibrate_tol=p["VIBRATE_TOL"], time_disc=TIME_DISC, gx=gx, gy=gy,
         one_plus_e=(1 + e),                    # physics.py:188

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FIZZ_ABI_VERSION 1
+#define FIZZ_ABI_VERSION 2
 
 #define FIZZ_MAX_FREE 8          /* free polygons per world (kernel instantiations F = 1..8)        */
 #define FIZZ_MAX_FIXED 16        /* fixed polygons per scene                                         */
@@ -74,6 +74,10 @@ typedef struct FizzParams {
     double one_minus_e2;   /* (1-ELASTICITY**2)             */
     double acc_x, acc_y;   /* sum([1*global_accel])/1  -> the acceleration Point.move() installs (physics.py:516) */
     double height;         /* World.height, for p_energy (physics.py:373) */
+    /* default-off extensions (absent from the reference, defined in csrc/fizz_ext.cuh): */
+    double friction_mu;    /* Coulomb coefficient of every contact; 0 = off (the reference has no friction) */
+    double ff_restitution; /* restitution between two FREE bodies (notes/collisions.tex:24-35); < 0 = off: the reference's
+                              perfectly elastic exchange that ignores ELASTICITY (physics.py:201-223) */
     int32_t max_calls;     /* watchdog: state-relevant check_collisions() calls per update(); >= 32 */
     int32_t reserved;
 } FizzParams;

@@ -221,6 +221,54 @@ static int check_collisions(fzo_world *w, hit *out) {
     return n;
 }
 
+/* ------------------------------------------------------------------------------------------------------------
+ * extensions: Coulomb friction and free-free restitution.  The reference has neither (SURVEY
+ * section 0, Q9); notes/collisions.tex:16-35 derives the restitution formula.  This is their DEFINITION, written
+ * independently of fizz2d_b200/csrc/fizz_ext.cuh from the same model:
+ *   t = (-u_y, u_x); the tangential (relative) velocity is reduced by an impulse of at most mu x the normal impulse,
+ *   sticking when less is enough; kinetic energy removed -> heat, so K + P + H stays constant.
+ * ------------------------------------------------------------------------------------------------------------ */
+static void ext_friction_fixed(double mu, double ope, double m1, double ux, double uy, double vdotN,
+                               double *vx, double *vy, double *heat) {
+    double tx = -uy, ty = ux;
+    double vt = dot2(*vx, *vy, tx, ty);
+    double lim = mu * (ope * fabs(vdotN));
+    double dvt = -vt, vt1;
+    if (fabs(vt) > lim) dvt = (vt > 0.0) ? -lim : lim;
+    *vx += dvt * tx;
+    *vy += dvt * ty;
+    vt1 = vt + dvt;
+    *heat += (.5 * m1) * (vt * vt - vt1 * vt1);
+}
+
+static void ext_restitution_free(double cr, double m1, double mprop1, double mprop2, double vn1, double vn2,
+                                 double *v1u, double *v2u, double *heat) {
+    double mean = mprop1 * vn1 + mprop2 * vn2;
+    double dvn = vn1 - vn2;
+    *v1u = mean + (mprop2 * cr) * (vn2 - vn1);
+    *v2u = mean + (mprop1 * cr) * (vn1 - vn2);
+    *heat += ((.5 * (m1 * mprop2)) * (1.0 - cr * cr)) * (dvn * dvn);
+}
+
+static void ext_friction_free(double mu, double cr_eff, double m1, double m2, double mprop2, double ux, double uy,
+                              double vn1, double vn2, double *v1x, double *v1y, double *v2x, double *v2y, double *heat) {
+    double tx = -uy, ty = ux;
+    double vt1 = dot2(*v1x, *v1y, tx, ty), vt2 = dot2(*v2x, *v2y, tx, ty);
+    double rel = vt1 - vt2;
+    double mred = m1 * mprop2;
+    double jmax = mu * (((1.0 + cr_eff) * fabs(vn1 - vn2)) * mred);
+    double jt = mred * fabs(rel);
+    double sj, dv1, dv2, w1, w2;
+    if (jt > jmax) jt = jmax;
+    sj = (rel > 0.0) ? -jt : jt;
+    dv1 = sj / m1;
+    dv2 = -(sj / m2);
+    *v1x += dv1 * tx; *v1y += dv1 * ty;
+    *v2x += dv2 * tx; *v2y += dv2 * ty;
+    w1 = vt1 + dv1; w2 = vt2 + dv2;
+    *heat += (.5 * m1) * (vt1 * vt1 - w1 * w1) + (.5 * m2) * (vt2 * vt2 - w2 * w2);
+}
+
 int fzo_update(fzo_world *w) {
     const fzo_params *p = &w->prm;
     int nf = w->nfree, k, v, ncol, c;
@@ -278,6 +326,8 @@ int fzo_update(fzo_world *w) {
                 o1->vy -= cc * uy;
                 H = .5 * o1->mass * p->one_minus_e2 * (vdotN * vdotN); /* :191 */
                 w->heat += H;                           /* :195 */
+                if (p->friction_mu > 0.0)               /* extension, off by default */
+                    ext_friction_fixed(p->friction_mu, p->one_plus_e, o1->mass, ux, uy, vdotN, &o1->vx, &o1->vy, &w->heat);
                 finish_update(o1);                      /* :197 */
                 w->ops += 20.0 + 2.0 * o1->n;
             } else {                                    /* :201-223 */
@@ -290,15 +340,20 @@ int fzo_update(fzo_world *w) {
                 vn1 = dot2(o1->vx, o1->vy, ux, uy);                      /* :207 */
                 vn2 = dot2(o2->vx, o2->vy, ux, uy);                      /* :208 */
                 v1u = (mprop1 - mprop2) * vn1 + 2 * mprop2 * vn2;        /* :209 */
+                v2u = 2 * mprop1 * vn1 + (mprop2 - mprop1) * vn2;        /* :218 (needs nothing computed in between) */
+                if (p->ff_restitution >= 0.0)                            /* extension, off by default */
+                    ext_restitution_free(p->ff_restitution, o1->mass, mprop1, mprop2, vn1, vn2, &v1u, &v2u, &w->heat);
                 d1 = v1u - dot2(o1->vx, o1->vy, ux, uy);                 /* :210 */
                 o1->vx += d1 * ux; o1->vy += d1 * uy;
                 for (v = 0; v < o1->n; v++) { o1->ptx[v] += mprop1 * nvx; o1->pty[v] += mprop1 * nvy; } /* :212 */
                 finish_update(o1);                                       /* :215 */
                 o2->px -= mprop2 * nvx; o2->py -= mprop2 * nvy;          /* :217 */
                 if (o2->snap_alias) { o2->sx = o2->px; o2->sy = o2->py; }
-                v2u = 2 * mprop1 * vn1 + (mprop2 - mprop1) * vn2;        /* :218 */
                 d2 = v2u - dot2(o2->vx, o2->vy, ux, uy);                 /* :219 */
                 o2->vx += d2 * ux; o2->vy += d2 * uy;
+                if (p->friction_mu > 0.0)                                /* extension, off by default */
+                    ext_friction_free(p->friction_mu, p->ff_restitution >= 0.0 ? p->ff_restitution : 1.0, o1->mass,
+                                      o2->mass, mprop2, ux, uy, vn1, vn2, &o1->vx, &o1->vy, &o2->vx, &o2->vy, &w->heat);
                 for (v = 0; v < o2->n; v++) { o2->ptx[v] -= mprop2 * nvx; o2->pty[v] -= mprop2 * nvy; } /* :221 */
                 finish_update(o2);                                       /* :223 */
                 w->ops += 40.0 + 2.0 * (o1->n + o2->n);

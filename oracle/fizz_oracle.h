@@ -8,6 +8,8 @@
  * Parity status: PINNED -- checked bit-for-bit against traces of the reference itself (run in the build
  * container through oracle/ref_harness.py) that are committed under tests/golden/.  The reference has no
  * tests or golden vectors of its own.
+ * The two default-off EXTENSIONS (friction_mu, ff_restitution) have no reference at all: for them this file is the
+ * definition the CUDA kernels are checked against ("parity unpinned" by construction; with both off, nothing changes).
  */
 #ifndef FIZZ_ORACLE_H
 #define FIZZ_ORACLE_H
@@ -29,6 +31,9 @@ typedef struct {
     double one_plus_e;    /* (1+ELASTICITY)      evaluated by Python on the host (physics.py:188) */
     double one_minus_e2;  /* (1-ELASTICITY**2)   evaluated by Python on the host (physics.py:191) */
     double height;        /* World.height, for p_energy (physics.py:373) */
+    /* default-off extensions -- NOT in the reference, defined by this project (see fizz_oracle.c "extensions"): */
+    double friction_mu;   /* Coulomb coefficient, 0 = off */
+    double ff_restitution;/* restitution between two free bodies, < 0 = off (reference: elastic exchange) */
     int max_calls;        /* watchdog: state-relevant check_collisions calls per update()       */
 } fzo_params;
 

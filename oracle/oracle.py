@@ -142,7 +142,8 @@ def body_constants(points, density, eps=1e-12):
 
 class _Params(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("elasticity", "epsilon", "time_tol", "collision_tol", "vibrate_tol",
-                                          "time_disc", "gx", "gy", "one_plus_e", "one_minus_e2", "height")] + \
+                                          "time_disc", "gx", "gy", "one_plus_e", "one_minus_e2", "height",
+                                          "friction_mu", "ff_restitution")] + \
                [("max_calls", C.c_int)]
 
 
@@ -185,11 +186,15 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def make_params(params=None, height=0, max_calls=4096, gravity=(0.0, 0.0)):
+def make_params(params=None, height=0, max_calls=4096, gravity=(0.0, 0.0), friction=None, ff_restitution=None):
+    """friction / ff_restitution: the default-off extensions; None = what `PARAM FRICTION` / `PARAM FF_RESTITUTION`
+    lines of the scene say, else off (0 / -1)."""
     p = dict(DEFAULT_PARAMS)
     p.update(params or {})
     e = p["ELASTICITY"]
-    return _Params(elasticity=e, epsilon=p["EPSILON"], time_tol=p["TIME_TOL"], collision_tol=p["COLLISION_TOL"],
+    mu = float(p.get("FRICTION", 0.0) if friction is None else friction)
+    ffr = float(p.get("FF_RESTITUTION", -1.0) if ff_restitution is None else ff_restitution)
+    return _Params(friction_mu=mu, ff_restitution=ffr, elasticity=e, epsilon=p["EPSILON"], time_tol=p["TIME_TOL"], collision_tol=p["COLLISION_TOL"],
                    vibrate_tol=p["VIBRATE_TOL"], time_disc=TIME_DISC, gx=float(gravity[0]), gy=float(gravity[1]),
                    one_plus_e=(1 + e), one_minus_e2=(1 - e**2), height=float(height), max_calls=int(max_calls))
 

@@ -13,7 +13,8 @@ def oracle_from_spec(spec, w, max_calls=None, trace_cap=0, gravity=None):
     """CPU-oracle world fed with the PRODUCT loader's constants for world w of a GroupSpec."""
     p = spec.params
     prm = orc.make_params(spec.scene.params, spec.height, max_calls if max_calls is not None else p.max_calls,
-                          gravity if gravity is not None else (p.gx, p.gy))
+                          gravity if gravity is not None else (p.gx, p.gy), friction=p.friction_mu,
+                          ff_restitution=p.ff_restitution)
     return orc.OracleWorld(spec.nverts_free, spec.nverts_fixed,
                            np.concatenate([spec.pos[:, w].reshape(-1, 2), spec.fixed_com]),
                            spec.vel[:, w].reshape(-1, 2), np.concatenate([spec.radius[:, w], spec.fixed_radius]),

@@ -31,9 +31,9 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_struct_sizes():
     L = flib.load()
-    assert L.fizz_abi_version() == 1
+    assert L.fizz_abi_version() == 2
     assert C.sizeof(flib.FizzContact) == 48
-    assert C.sizeof(flib.FizzParams) == 13 * 8 + 8
+    assert C.sizeof(flib.FizzParams) == 15 * 8 + 8
 
 
 def _desc(F=2, X=1, nv=(4, 3, 4)):
