@@ -461,9 +461,10 @@ class BatchedWorld:
         """Execution strategy (results never depend on it): "hybrid" = ballistic thread-per-world kernel +
         warp-per-world contact kernel per chunk of timesteps, trapped worlds on their own "runner" launches that do not
         stop at chunk boundaries; "hybrid_sync" = the same without runners; "hybrid3" = plus a thread-per-world
-        separation prover tier (busy scenes, use small chunks); "thread" = one thread-per-world kernel."""
+        separation prover tier (busy scenes, use small chunks); "thread" = one thread-per-world kernel;
+        "thread_fp32" = that kernel in single precision, the one mode whose results DO differ (optional FP32 mode)."""
         m = {"hybrid": _lib.MODE_HYBRID, "thread": _lib.MODE_THREAD, "hybrid3": _lib.MODE_HYBRID3,
-             "hybrid_sync": _lib.MODE_HYBRID_SYNC}[mode]
+             "hybrid_sync": _lib.MODE_HYBRID_SYNC, "thread_fp32": _lib.MODE_THREAD_FP32}[mode]
         for g in self.groups:
             _lib.check(_lib.load().fizz_set_tuning(g.handle, m, int(chunk_steps)))
 

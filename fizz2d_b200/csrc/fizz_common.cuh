@@ -56,7 +56,8 @@ struct KParams {
 #define FIZZ_ASSERT(cond) ((void)0)
 #endif
 
-__device__ __forceinline__ double dot2(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
+template <typename T>
+__device__ __forceinline__ T dot2(T a0, T a1, T b0, T b1) { return fma(a1, b1, a0 * b0); }
 
 __device__ __forceinline__ void trace_hit(const KParams &kp, long long w, long long step, int call, int i, int j,
                                           double nx, double ny, double mag) {

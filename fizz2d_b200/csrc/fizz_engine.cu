@@ -9,7 +9,8 @@
 //     on library-owned streams step them to the end of the fizz_step() call (see fizz_step).
 //   FIZZ_MODE_HYBRID_SYNC: the same without runner launches.
 //   FIZZ_MODE_HYBRID3: adds the separation-prover tier and runs two contact-kernel instances side by side.
-//   FIZZ_MODE_THREAD: step_kernel<F> -- thread per world, full semantics in one launch.
+//   FIZZ_MODE_THREAD: step_kernel<F, double> -- thread per world, full semantics in one launch.
+//   FIZZ_MODE_THREAD_FP32: step_kernel<F, float> -- the same operation sequence in single precision (optional mode).
 // Also here: the batched rasteriser's entry points (fizz_raster.cuh).
 #include "fizz_b200.h"
 
@@ -113,12 +114,13 @@ cudaError_t raise_dynamic_smem(K kernel, size_t smem, size_t *current) {
 
 template <int F>
 cudaError_t prep_thread(size_t smem, KernelInfo *ki) {
-    static size_t current[MAX_DEVICES] = {};
-    cudaError_t e = raise_dynamic_smem(step_kernel<F>, smem, current);
+    static size_t current[MAX_DEVICES] = {}, current32[MAX_DEVICES] = {};
+    cudaError_t e = raise_dynamic_smem(step_kernel<F, double>, smem, current);
+    if (e == cudaSuccess) e = raise_dynamic_smem(step_kernel<F, float>, smem, current32);   // (same size: simpler)
     if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&ki->attr, step_kernel<F>);
+    e = cudaFuncGetAttributes(&ki->attr, step_kernel<F, double>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, step_kernel<F>, BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki->blocks_per_sm, step_kernel<F, double>, BLOCK, smem);
 }
 // The lean variant must work; the prover variant (FIZZ_MODE_HYBRID3 only) needs shared memory that a vertex-rich scene
 // may not leave: then only that mode is unavailable (*prover_ok = false), the group is still created.
@@ -474,9 +476,10 @@ int fizz_profile_read(FizzGroup *g, double *ms, int64_t *launches, int32_t reset
 
 int fizz_set_tuning(FizzGroup *g, int32_t mode, int64_t chunk_steps) {
     if (!g) return fail(FIZZ_E_ARG, "fizz_set_tuning: null group");
-    if (mode != FIZZ_MODE_HYBRID && mode != FIZZ_MODE_THREAD && mode != FIZZ_MODE_HYBRID3 && mode != FIZZ_MODE_HYBRID_SYNC)
+    if (mode != FIZZ_MODE_HYBRID && mode != FIZZ_MODE_THREAD && mode != FIZZ_MODE_HYBRID3 && mode != FIZZ_MODE_HYBRID_SYNC &&
+        mode != FIZZ_MODE_THREAD_FP32)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: unknown mode");
-    if (mode == FIZZ_MODE_THREAD && !g->thread_ok)
+    if ((mode == FIZZ_MODE_THREAD || mode == FIZZ_MODE_THREAD_FP32) && !g->thread_ok)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: thread mode does not fit in shared memory for this topology");
     if (mode == FIZZ_MODE_HYBRID3 && !g->prover_ok)
         return fail(FIZZ_E_ARG, "fizz_set_tuning: hybrid3 mode: the prover tier does not fit in shared memory for this topology");
@@ -546,12 +549,16 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     CU(cudaSetDevice(g->device));
     KParams kp = g->kp;
     const int F = kp.F;
-    if (g->mode == FIZZ_MODE_THREAD) {
+    if (g->mode == FIZZ_MODE_THREAD || g->mode == FIZZ_MODE_THREAD_FP32) {
         g->target += n_steps;
         kp.target_steps = g->target;
         dim3 grid((unsigned)(g->lay.stride / BLOCK));
         cudaEvent_t ea = g->profile ? next_event(g, st) : nullptr;
-        FIZZ_DISPATCH_F(F, (step_kernel<FF><<<grid, BLOCK, g->thread_smem, st>>>(kp)));
+        if (g->mode == FIZZ_MODE_THREAD) {
+            FIZZ_DISPATCH_F(F, (step_kernel<FF, double><<<grid, BLOCK, g->thread_smem, st>>>(kp)));
+        } else {
+            FIZZ_DISPATCH_F(F, (step_kernel<FF, float><<<grid, BLOCK, g->thread_smem, st>>>(kp)));
+        }
         if (g->profile) {
             cudaEvent_t eb = next_event(g, st);
             if (ea && eb) g->spans.push_back({FIZZ_KERNEL_THREAD, ea, eb});

@@ -21,47 +21,47 @@ namespace fizz {
 
 // Free body (mass m1, velocity v after the reference's normal update :188) against a FIXED body.
 // ope = (1 + ELASTICITY), vdotN = v.u before the update (:183): the normal impulse per unit mass is ope * |vdotN|.
-__device__ __forceinline__ void ext_friction_fixed(double mu, double ope, double m1, double ux, double uy, double vdotN,
-                                                   double &vx, double &vy, double &heat) {
-    const double tx = -uy, ty = ux;
-    const double vt = dot2(vx, vy, tx, ty);
-    const double lim = mu * (ope * fabs(vdotN));
-    double dvt = -vt;                                   // stick
-    if (fabs(vt) > lim) dvt = (vt > 0.0) ? -lim : lim;  // slide
+template <typename T>
+__device__ __forceinline__ void ext_friction_fixed(T mu, T ope, T m1, T ux, T uy, T vdotN, T &vx, T &vy, T &heat) {
+    const T tx = -uy, ty = ux;
+    const T vt = dot2(vx, vy, tx, ty);
+    const T lim = mu * (ope * fabs(vdotN));
+    T dvt = -vt;                                   // stick
+    if (fabs(vt) > lim) dvt = (vt > T(0)) ? -lim : lim;  // slide
     vx += dvt * tx;
     vy += dvt * ty;
-    const double vt1 = vt + dvt;
-    heat += (.5 * m1) * (vt * vt - vt1 * vt1);
+    const T vt1 = vt + dvt;
+    heat += (T(.5) * m1) * (vt * vt - vt1 * vt1);
 }
 
 // Normal velocities after a free-free contact with restitution c_r (replaces :209 and :218).
-__device__ __forceinline__ void ext_restitution_free(double cr, double m1, double mprop1, double mprop2, double vn1,
-                                                     double vn2, double &v1u, double &v2u, double &heat) {
-    const double mean = mprop1 * vn1 + mprop2 * vn2;
+template <typename T>
+__device__ __forceinline__ void ext_restitution_free(T cr, T m1, T mprop1, T mprop2, T vn1, T vn2, T &v1u, T &v2u, T &heat) {
+    const T mean = mprop1 * vn1 + mprop2 * vn2;
     v1u = mean + (mprop2 * cr) * (vn2 - vn1);
     v2u = mean + (mprop1 * cr) * (vn1 - vn2);
-    const double dvn = vn1 - vn2;
-    heat += ((.5 * (m1 * mprop2)) * (1.0 - cr * cr)) * (dvn * dvn);
+    const T dvn = vn1 - vn2;
+    heat += ((T(.5) * (m1 * mprop2)) * (T(1) - cr * cr)) * (dvn * dvn);
 }
 
 // Coulomb friction between two free bodies, applied to their velocities after the normal exchange.
 // vn1, vn2 = normal velocities BEFORE the exchange; cr_eff = the restitution that exchange used (1 for the reference's).
-__device__ __forceinline__ void ext_friction_free(double mu, double cr_eff, double m1, double m2, double mprop2, double ux,
-                                                  double uy, double vn1, double vn2, double &v1x, double &v1y, double &v2x,
-                                                  double &v2y, double &heat) {
-    const double tx = -uy, ty = ux;
-    const double vt1 = dot2(v1x, v1y, tx, ty), vt2 = dot2(v2x, v2y, tx, ty);
-    const double rel = vt1 - vt2;
-    const double mred = m1 * mprop2;                    // m1 m2 / (m1 + m2)
-    const double jmax = mu * (((1.0 + cr_eff) * fabs(vn1 - vn2)) * mred);
-    double jt = mred * fabs(rel);                       // stick
+template <typename T>
+__device__ __forceinline__ void ext_friction_free(T mu, T cr_eff, T m1, T m2, T mprop2, T ux, T uy, T vn1, T vn2, T &v1x,
+                                                  T &v1y, T &v2x, T &v2y, T &heat) {
+    const T tx = -uy, ty = ux;
+    const T vt1 = dot2(v1x, v1y, tx, ty), vt2 = dot2(v2x, v2y, tx, ty);
+    const T rel = vt1 - vt2;
+    const T mred = m1 * mprop2;                    // m1 m2 / (m1 + m2)
+    const T jmax = mu * (((T(1) + cr_eff) * fabs(vn1 - vn2)) * mred);
+    T jt = mred * fabs(rel);                       // stick
     if (jt > jmax) jt = jmax;                           // slide
-    const double sj = (rel > 0.0) ? -jt : jt;           // tangential impulse on body 1
-    const double dv1 = sj / m1, dv2 = -(sj / m2);
+    const T sj = (rel > T(0)) ? -jt : jt;           // tangential impulse on body 1
+    const T dv1 = sj / m1, dv2 = -(sj / m2);
     v1x += dv1 * tx; v1y += dv1 * ty;
     v2x += dv2 * tx; v2y += dv2 * ty;
-    const double w1 = vt1 + dv1, w2 = vt2 + dv2;
-    heat += (.5 * m1) * (vt1 * vt1 - w1 * w1) + (.5 * m2) * (vt2 * vt2 - w2 * w2);
+    const T w1 = vt1 + dv1, w2 = vt2 + dv2;
+    heat += (T(.5) * m1) * (vt1 * vt1 - w1 * w1) + (T(.5) * m2) * (vt2 * vt2 - w2 * w2);
 }
 
 }  // namespace fizz

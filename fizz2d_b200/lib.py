@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("FIZZ_B200_LIB") or os.path.join(HERE, "libfizz_b200.s
 
 MAX_FREE, MAX_FIXED, MAX_POLY_VERTS, MAX_FIXED_VERTS, MAX_HITS = 8, 16, 16, 96, 32
 ST_RUNNING, ST_CAPPED, ST_NONFINITE, ST_HIT_OVERFLOW = 0, 1, 2, 3
-MODE_THREAD, MODE_HYBRID, MODE_HYBRID3, MODE_HYBRID_SYNC = 0, 1, 2, 3
+MODE_THREAD, MODE_HYBRID, MODE_HYBRID3, MODE_HYBRID_SYNC, MODE_THREAD_FP32 = 0, 1, 2, 3, 4
 KERNEL_THREAD, KERNEL_BALLISTIC, KERNEL_CONTACT, KERNEL_PROVER, KERNEL_TRAPPED = 0, 1, 2, 3, 4
 
 dp = C.POINTER(C.c_double)

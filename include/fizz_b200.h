@@ -42,6 +42,10 @@ extern "C" {
                                longest sequential chain never waits at a chunk boundary (default)             */
 #define FIZZ_MODE_HYBRID_SYNC 3 /* the same without runners: every world stops at every chunk boundary      */
 #define FIZZ_MODE_THREAD 0  /* one thread-per-world kernel with the full semantics                        */
+#define FIZZ_MODE_THREAD_FP32 4 /* OPTIONAL single-precision mode: the thread-per-world kernel with every operation of
+                               update() carried out in FP32 (state still stored as FP64 in the slab, converted on load
+                               and store).  Not bit-compatible with the reference: positions follow the FP64 path to
+                               ~1e-6 relative until the first contact decision differs (measured horizon) */
 #define FIZZ_MODE_HYBRID3 2 /* throughput-tuned: adds a thread-per-world "separation prover" tier and splits the contact
                                kernel into a compact high-occupancy general instance and a trapped instance that run
                                side by side: best for busy scenes (use small chunks, e.g. 32)                   */

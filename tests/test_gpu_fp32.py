@@ -1,0 +1,62 @@
+"""GPU: the optional single-precision mode ("thread_fp32": every operation of update() in FP32, EPSILON raised to 1e-3 px)
+against the FP64 path on samples of BASELINE configs 2 and 3.  Nothing is bit-compatible here; the documented bound
+(measured with tools/fp32_probe.py) is what these tests hold it to:
+  * while the contact decisions of a world agree with FP64 (same check_collisions() count every timestep), its positions
+    stay within 2e-4 of the scene size (measured: median 3e-6, p99 1e-5 on config 2);
+  * total energy K + P + H of every uncapped world drifts by less than 1e-5 relative over 300 timesteps (measured: 6e-7
+    max on config 2, 2e-6 on config 3);
+  * contact-decision divergence horizon: config 2 -- at least 85 % of the worlds never diverge in 300 timesteps (measured
+    93 %); config 3 (contacts from timestep 0, knife-edge halving decisions) -- median horizon of at least 5 timesteps
+    (measured 30)."""
+import numpy as np
+import pytest
+
+import fizz2d_b200 as fz
+from conftest import scene_file
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(scene, seed, n, steps, mode):
+    bw = fz.BatchedWorld.from_in(scene_file(scene), n_worlds=n, perturb=True, seed=seed, max_calls=256)
+    bw.set_tuning(mode, 256)
+    calls, com, e0 = [], [], bw.energy()
+    for t in range(steps):
+        bw.step(1)
+        calls.append(bw.calls())
+        com.append(bw.com()[:, :, 0:2])
+    return np.array(calls), np.array(com), e0, bw.energy(), bw.status()
+
+
+@pytest.mark.parametrize("scene,seed,n,min_never,min_median", [("BOX_1SQUAREFRICTION", 20260002, 512, 0.85, 300),
+                                                               ("RAMPWORLD_2TRIANGLES_5SQUARES", 20260003, 256, 0.0, 5)])
+def test_fp32_mode_against_fp64(scene, seed, n, min_never, min_median):
+    steps = 300
+    c64, x64, _, _, s64 = _run(scene, seed, n, steps, "thread")
+    c32, x32, e0, e1, s32 = _run(scene, seed, n, steps, "thread_fp32")
+    diff = c64 != c32
+    horizon = np.where(diff.any(axis=0), diff.argmax(axis=0), steps)
+    assert (horizon == steps).mean() >= min_never and np.median(horizon) >= min_median, np.percentile(horizon, [0, 10, 50, 90])
+    same = np.nonzero(horizon == steps)[0]
+    if len(same):
+        scale = float(np.abs(x64[:, same]).max())
+        err = np.abs(x32[:, same] - x64[:, same]).reshape(steps, len(same), -1).max(axis=(0, 2)) / scale
+        assert np.percentile(err, 90) < 2e-4, np.percentile(err, [50, 90, 100])
+    ok = (s32 == 0) & (e0[:, 0] > 0)
+    assert ok.sum() > n // 2
+    drift = np.abs(e1[ok, 0] - e0[ok, 0]) / e0[ok, 0]
+    assert drift.max() < 1e-5, drift.max()
+    assert abs(int((s32 != 0).sum()) - int((s64 != 0).sum())) <= max(4, n // 10)     # the watchdog trips about as often
+
+
+def test_fp32_mode_is_a_mode_not_a_default():
+    """The slab stays FP64 and the default modes are untouched: stepping in FP32 and then in FP64 continues from the
+    rounded state without error; the FP64 modes never run single-precision code."""
+    bw = fz.BatchedWorld.from_in(scene_file("BOX_1SQUARE"), n_worlds=8, perturb=True, seed=4)
+    bw.set_tuning("thread_fp32", 1)
+    bw.step(20)
+    a = bw.com()
+    assert np.array_equal(a, a.astype(np.float32).astype(np.float64))       # state was rounded to float on store
+    bw.set_tuning("hybrid", 64)
+    bw.step(20)
+    assert (bw.steps_done() == 40).all()
