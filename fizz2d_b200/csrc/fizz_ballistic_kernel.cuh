@@ -165,8 +165,46 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
     int empty_streak = 0;      // consecutive steps without any candidate pair
     if constexpr (!PROVER) {
         // ---- lean variant: integer-pipe threshold tests folded into one predicate, in-place move ---------------------
-        while (step < kp.target_steps) {
+        // Non-finite coordinates (whose pairs the reference does NOT skip: `nan > r` is False, physics.py:278) cannot
+        // appear inside this launch when every |pos|, |vel dt| and |acc dt^2| starts below 2^993: n steps move a coordinate
+        // by at most n |v dt| + n^2 |a dt^2|, and no launch makes 2^20 steps.  Anything larger (or non-finite already)
+        // goes to the contact kernel, which tests every step; so the loop below carries no exponent test.
+        {
+            unsigned big = 0;
+#pragma unroll
+            for (int b = 0; b < F; b++) {
+                big |= (((unsigned)__double2hiint(px[b]) & 0x7ff00000u) >= 0x7e000000u) | (((unsigned)__double2hiint(py[b]) & 0x7ff00000u) >= 0x7e000000u);
+                big |= (((unsigned)__double2hiint(vx[b]) & 0x7ff00000u) >= 0x7e000000u) | (((unsigned)__double2hiint(vy[b]) & 0x7ff00000u) >= 0x7e000000u);
+            }
+            big |= (((unsigned)__double2hiint(kp.accx) & 0x7ff00000u) >= 0x7e000000u) | (((unsigned)__double2hiint(kp.accy) & 0x7ff00000u) >= 0x7e000000u);
+            if (big) handed_over = true;
+        }
+        // One test per free body for ALL its pairs with fixed bodies.  With (hb, hh) the centre and half extents of the box
+        // around the fixed centres and R >= max(r_i, r_j) for every fixed j:  |x_i - hb_x| > hh_x + R  implies
+        // |x_i - c_j,x| > R for every j, hence norm(d) > max(r_i, r_j): the reference skips each of those pairs (:277-279),
+        // and so does the exact test on fma(dy, dy, dx dx) (a margin of 2^-17 on R covers every rounding on the way, and
+        // the one-unit gap in the high word that the tests below ask for).  Same for y.  Compared on the integer pipe.
+        int qx_h[F], qy_h[F];
+        {
+            const double grow = 1.0 + 1.0 / 131072.0;
+#pragma unroll
+            for (int b = 0; b < F; b++) {
+                const double r = sqrt(thr[b]);                          // radius of body b, to an ulp
+                const double R = (r > kp.frmax) ? r : kp.frmax;         // (NaN radius: the comparisons below fail, no reject)
+                qx_h[b] = __double2hiint((kp.hhx + R) * grow + 1e-6) + 1;   // (+1e-6 px: the hull's own rounding)
+                qy_h[b] = __double2hiint((kp.hhy + R) * grow + 1e-6) + 1;
+                if (!(R == R) || !(R < 1e300)) { qx_h[b] = 0x7fffffff; qy_h[b] = 0x7fffffff; }
+            }
+        }
+        // the broad phase of one timestep: does any pair pass (conservatively)?
+        auto candidates = [&]() -> bool {
             bool any = false;
+            bool near_fixed = false;
+#pragma unroll
+            for (int i = 0; i < F; i++) {
+                const int ex = __double2hiint(px[i] - kp.hbx) & 0x7fffffff, ey = __double2hiint(py[i] - kp.hby) & 0x7fffffff;
+                near_fixed |= !((ex > qx_h[i]) | (ey > qy_h[i]));
+            }
 #pragma unroll
             for (int i = 0; i < F; i++) {
 #pragma unroll
@@ -176,31 +214,50 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
                     any |= !(sh > max(thr_h[i], thr_h[j]));
                 }
             }
-            for (int j = 0; j < X; j++) {
-                const double cx = kp.fcx[j], cy = kp.fcy[j];
-                const int fh = __double2hiint(kp.fthr[j]);
+            if (near_fixed) {
+                for (int j = 0; j < X; j++) {
+                    const double cx = kp.fcx[j], cy = kp.fcy[j];
+                    const int fh = __double2hiint(kp.fthr[j]);
 #pragma unroll
-                for (int i = 0; i < F; i++) {
-                    const double dx = px[i] - cx, dy = py[i] - cy;
-                    const int sh = __double2hiint(fma(dy, dy, dx * dx));
-                    any |= !(sh > max(thr_h[i], fh));
+                    for (int i = 0; i < F; i++) {
+                        const double dx = px[i] - cx, dy = py[i] - cy;
+                        const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                        any |= !(sh > max(thr_h[i], fh));
+                    }
                 }
             }
-            unsigned expo = 0;
-#pragma unroll
-            for (int b = 0; b < F; b++) {
-                const unsigned hx = (unsigned)__double2hiint(px[b]) & 0x7ff00000u, hy = (unsigned)__double2hiint(py[b]) & 0x7ff00000u;
-                expo |= (hx == 0x7ff00000u) | (hy == 0x7ff00000u);
-            }
-            any |= expo != 0;
-            if (any) { handed_over = true; break; }  // candidates (or NaN): the prover variant looks at this step
+            return any;
+        };
+        auto full_move = [&]() {
 #pragma unroll
             for (int b = 0; b < F; b++) {
                 double nx_, ny_, nvx_, nvy_;
                 FIZZ_MOVE_POINT(px[b], py[b], vx[b], vy[b], dt, kp.accx, kp.accy, kp.accx, kp.accy, nx_, ny_, nvx_, nvy_);
                 px[b] = nx_; py[b] = ny_; vx[b] = nvx_; vy[b] = nvy_;
             }
-            step++;
+        };
+        // Without gravity Point.move (:502-529) is v + 0.0, x + v dt, v + 0.0: after ONE complete move a velocity is no
+        // longer -0.0 (the only value v + 0.0 changes), so every further move of the launch is x += v dt, bit for bit.
+        const bool nograv = (kp.accx == 0.0) && (kp.accy == 0.0);
+        if (!handed_over && step < kp.target_steps) {
+            if (candidates()) handed_over = true;
+            else { full_move(); step++; }
+        }
+        if (!handed_over) {
+            if (nograv) {
+                while (step < kp.target_steps) {
+                    if (candidates()) { handed_over = true; break; }  // candidates: the next tier looks at this step
+#pragma unroll
+                    for (int b = 0; b < F; b++) { px[b] = px[b] + vx[b] * dt; py[b] = py[b] + vy[b] * dt; }
+                    step++;
+                }
+            } else {
+                while (step < kp.target_steps) {
+                    if (candidates()) { handed_over = true; break; }
+                    full_move();
+                    step++;
+                }
+            }
         }
     } else {
         while (step < kp.target_steps) {

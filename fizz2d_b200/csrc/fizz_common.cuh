@@ -36,6 +36,9 @@ struct KParams {
     int swl;                   // log2 of the narrow phase's slot width: 8, 16 or 32 lanes >= the largest n1 + n2 of the scene
     int nv[TAB], vs[TAB];      // vertices per body / first vertex (free: into the world's rows, fixed: into fixed_geom)
     double fcx[FIZZ_MAX_FIXED], fcy[FIZZ_MAX_FIXED], fthr[FIZZ_MAX_FIXED];
+    // hull of the fixed bodies' centres (centre, half extents) and their largest radius: one conservative test per free
+    // body rejects all its pairs with fixed bodies at once (fizz_ballistic_kernel.cuh)
+    double hbx, hby, hhx, hhy, frmax;
     double coll_tol, time_tol, eps, vib_tol, time_disc, ope, ome2, accx, accy;
     double mu, ffr;            // extensions (fizz_ext.cuh): Coulomb coefficient (0 = off), free-free restitution (< 0 = off)
     double vib_thr;            // T(vib_tol): norm(nv) > VIBRATE_TOL  <=>  fma(nvy,nvy,nvx*nvx) > vib_thr  (:180)

@@ -371,6 +371,18 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
             o6[0] = xy[2 * k]; o6[1] = xy[2 * k + 1]; o6[2] = nx; o6[3] = ny; o6[4] = lo; o6[5] = hi;
         }
     }
+    {
+        double xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY, rmax = 0.0;
+        for (int j = 0; j < X; j++) {
+            xlo = std::min(xlo, kp.fcx[j]); xhi = std::max(xhi, kp.fcx[j]);
+            ylo = std::min(ylo, kp.fcy[j]); yhi = std::max(yhi, kp.fcy[j]);
+            const double r = std::sqrt(kp.fthr[j]);     // T(r) <= r^2 (1 + 2^-52): sqrt(T) is r to an ulp; NaN stays NaN
+            rmax = (r > rmax || r != r) ? r : rmax;
+        }
+        kp.hbx = X ? .5 * (xlo + xhi) : 0.0; kp.hby = X ? .5 * (ylo + yhi) : 0.0;
+        kp.hhx = X ? .5 * (xhi - xlo) : 0.0; kp.hhy = X ? .5 * (yhi - ylo) : 0.0;
+        kp.frmax = rmax;
+    }
     cudaError_t e = cudaMemcpy(fixed_dev, fg, sizeof(double) * (size_t)vfix * 6, cudaMemcpyHostToDevice);
     delete[] fg;
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMemcpy(fixed scene)"); }
