@@ -28,6 +28,7 @@ struct KParams {
     const double *fixed_geom;  // [FV][6]: x, y, unit normal of edge k->k+1 (nx, ny), own projection (lo, hi)
     unsigned long long *counters;  // [0] world-steps advanced by the ballistic kernel, [1] by the contact kernel,
                                    // [2] check_collisions() made by the contact kernel, [3] of those in the fast path
+    long long *general_calls;      // optional, per world: check_collisions() made OUTSIDE the single-contact fast path
     FizzContact *trace;
     unsigned long long *trace_count;
     long long trace_cap;

@@ -274,16 +274,21 @@ enum { TRAP_MIDSTEP = 0, TRAP_EMPTY = 1, TRAP_BOUNDARY = 2 };
 // which changes neither a minimum nor a maximum of projections -- one instruction stream for both shapes (the kernel is
 // bound by instruction fetch wherever it is not bound by this chain).  MULTI = false: the variant of the throughput
 // instance, which leaves update()'s end and the next timestep to the general path (smaller footprint).
-template <bool MULTI>
+// TRACK = true (with MULTI = false): additionally reports the bounding box of b's centre of mass over the loop -- for the
+// caller that runs the resolve loops of TWO trapped bodies one after the other (see the contact kernel).
+struct TrapBox { double xlo, xhi, ylo, yhi; };
+template <bool MULTI, bool TRACK = false>
 __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
                                            double &heat, int &ncalls, long long &ncalls_total, long long &step, int &k,
-                                           double &dt, int &steps_here, int &last_calls, const int kstar, const double dtk) {
+                                           double &dt, int &steps_here, int &last_calls, const int kstar, const double dtk,
+                                           TrapBox *box = nullptr) {
     constexpr int NM = 4;
     const unsigned FULL = 0xffffffffu;
     const int n1 = kp.nv[b];
     const int v1 = kp.vs[b];
     FIZZ_ASSERT(b >= 0 && b < F && (n1 == 3 || n1 == 4));
     double cpx = s.px[b], cpy = s.py[b], cvx = s.vx[b], cvy = s.vy[b];
+    [[maybe_unused]] double bxlo = cpx, bxhi = cpx, bylo = cpy, byhi = cpy;
     const double m1 = s.mass[b], thr_b = s.thr[b];
     // this lane's broad-phase partner: body `lane` of objs+fixed_objs.  (a-b)^2 == (b-a)^2 exactly, so the order of
     // the subtraction at :277 does not matter.
@@ -410,6 +415,10 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
             // :180-181 norm(nv) > VIBRATE_TOL.  The latency-tuned variant only applies pushes that are certainly longer
             // (see gate_min below): no test here
             if (MULTI || fma(pnvy, pnvy, pnvx * pnvx) > vthr_r) { cpx += pnvx; cpy += pnvy; }
+            if constexpr (TRACK) {
+                bxlo = (cpx < bxlo) ? cpx : bxlo; bxhi = (cpx > bxhi) ? cpx : bxhi;
+                bylo = (cpy < bylo) ? cpy : bylo; byhi = (cpy > byhi) ? cpy : byhi;
+            }
             const double vdotN = dot2(cvx, cvy, pux, puy);                           // :183
             const double cc = ope_r * vdotN;                                         // :188
             cvx -= cc * pux;
@@ -657,6 +666,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
     if (lane == 0) {
         s.px[b] = cpx; s.py[b] = cpy; s.vx[b] = cvx; s.vy[b] = cvy; s.sx[b] = cpx; s.sy[b] = cpy;
     }
+    if constexpr (TRACK) { box->xlo = bxlo; box->xhi = bxhi; box->ylo = bylo; box->yhi = byhi; }
     __syncwarp();
     return ret;
 }
@@ -756,7 +766,8 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
         bool resolve = false, verts_explicit = false;
         int k = 0, ncalls = 0, ns = 0;
         int fast_step = 0, calm = 0;  // tier-3 bookkeeping (scheduling hint only)
-        int last_calls = 0;           // check_collisions() of the last completed timestep, saturated (scheduling hint only)
+        int last_calls = 0;           // check_collisions() of the last completed timestep (scheduling hint only)
+        [[maybe_unused]] int two_fail = 0;  // consecutive failed attempts at the two-trapped-bodies shortcut
         bool trapped = false;
         int quiet = 0;        // consecutive contact-free timesteps: one check_collisions(), no tuple (scheduling hint)
         int quiet_empty = 0;  // ... of those, consecutive ones whose broad phase was empty
@@ -1094,6 +1105,95 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 }
                 resolve = true;  // next round: check_collisions() at :234
 #ifndef FIZZ_NO_TRAP
+                if constexpr (FAST) {
+                    // ---- TWO bodies trapped at once, each against fixed bodies --------------------------------------------
+                    // Every check_collisions() of the resolve loop returns [(A, fixed), (B, fixed)] until one of them is out.
+                    // A resolve pass applies each tuple to its own body and nothing else moves, so A's sequence of pushes
+                    // is the one it would make alone, and so is B's -- provided the pair (A, B) stays outside the broad
+                    // phase for every position the two go through (checked afterwards on the bounding boxes of the two
+                    // trajectories; a failed check restores both bodies and the general path runs the loop).  The loop then
+                    // makes max(n_A, n_B) checks.  Heat is added tuple by tuple in list order, which the two separate loops
+                    // cannot reproduce: only taken when ELASTICITY == 1 (every term is +0; a non-finite one restores too).
+                    if (speculate && nh == 2 && SW == 8 && two_fail < 2 && s.hj[0] >= F && s.hj[1] >= F && s.hi[0] != s.hi[1] &&
+                        kp.ome2 == 0.0 && !(kp.mu > 0.0)) {
+                        const int bA = s.hi[0], bB = s.hi[1];
+                        const int nA = kp.nv[bA], nB = kp.nv[bB];
+                        if ((nA == 3 || nA == 4) && (nB == 3 || nB == 4)) {
+                            // this lane's share of what a failed attempt has to put back
+                            double *slotp = nullptr;
+                            if (lane < 2 * nA) slotp = s.vert + 2 * kp.vs[bA] + lane;
+                            else if (lane >= 8 && lane < 8 + 2 * nB) slotp = s.vert + 2 * kp.vs[bB] + (lane - 8);
+                            else if (lane >= 16 && lane < 28) {
+                                const int bb = (lane < 22) ? bA : bB, f = (lane - 16) % 6;
+                                slotp = (f == 0 ? s.px : f == 1 ? s.py : f == 2 ? s.vx : f == 3 ? s.vy : f == 4 ? s.sx : s.sy) + bb;
+                            }
+                            const double saved = slotp ? *slotp : 0.0;
+                            const int nc0 = ncalls;
+                            const long long tot0 = ncalls_total;
+                            int sh = 0, lc = 0, kk2 = k;
+                            long long st2 = step;
+                            double dt2 = dt;
+                            TrapBox boxes[2];
+                            // A's loop, then B's.  A run ends EMPTY (its :234 check found b free: counted) or MIDSTEP (it stands
+                            // right before a check it could not classify: not counted).  The joint state the general path can
+                            // continue from must have both bodies at the SAME check: a body that is out of contact stays where
+                            // it is, so "A empty after pa checks, B before its check pb + 1 > pa" is such a state, and so is
+                            // "A before check pa + 1, B run for at most pa checks" (B's budget is cut to pa).
+                            int cons[2] = {0, 0}, rets[2] = {TRAP_MIDSTEP, TRAP_MIDSTEP};
+                            bool valid = true;
+#pragma unroll 1
+                            for (int which = 0; which < 2 && valid; which++) {     // (one call site: instruction footprint)
+                                long long tot = tot0;
+                                double hx = 0.0;
+                                int nc_in = nc0;
+                                if (which == 1 && rets[0] == TRAP_MIDSTEP) nc_in = kp.max_calls - cons[0];   // budget = pa checks
+                                int nc = nc_in;
+                                rets[which] = trapped_run<false, true>(s, kp, F, X, lane, which ? bB : bA, hx, nc, tot, st2, kk2, dt2, sh,
+                                                                       lc, kstar_all, dtk_all, &boxes[which]);
+                                cons[which] = nc - nc_in;
+                                valid = (hx == 0.0) && (which == 1 || rets[0] == TRAP_EMPTY || cons[0] >= 1);
+                            }
+                            const TrapBox boxA = boxes[0], boxB = boxes[1];
+                            const int pa = cons[0], pb = cons[1];
+                            int joint = -1;   // checks consumed by the joint state, or -1
+                            bool finished = false;
+                            if (valid) {
+                                if (rets[0] == TRAP_EMPTY && rets[1] == TRAP_EMPTY) { joint = pa > pb ? pa : pb; finished = true; }
+                                else if (rets[0] == TRAP_EMPTY && pb >= pa) joint = pb;
+                                else if (rets[0] == TRAP_MIDSTEP && ((rets[1] == TRAP_EMPTY && pb <= pa) || (rets[1] == TRAP_MIDSTEP && pb == pa)))
+                                    joint = pa;
+                                valid = joint >= 0;
+                            }
+                            if (valid) {
+                                // no position of A's trajectory within max(r_A, r_B) of any position of B's (:277-279)
+                                const double gx = fmax(fmax(boxA.xlo - boxB.xhi, boxB.xlo - boxA.xhi), 0.0);
+                                const double gy = fmax(fmax(boxA.ylo - boxB.yhi, boxB.ylo - boxA.yhi), 0.0);
+                                const double tm = fmax(s.thr[bA], s.thr[bB]) * 1.000001 + 1e-9;
+                                valid = (gx * gx > tm) || (gy * gy > tm);
+                            }
+                            if (valid) {
+                                ncalls = nc0 + joint;
+                                ncalls_total = tot0 + joint;
+                                fast_calls += joint;
+                                fast_step += joint;
+                                verts_explicit = true;
+                                two_fail = 0;
+                                if (finished) goto end_of_update;   // the :234 call that found nothing has been made
+                                continue;                           // the general path makes the next check of this loop
+                            }
+#ifdef FIZZ_DEBUG_TWO
+                            if (lane == 0 && step < 400)
+                                printf("two-body attempt failed: w %lld step %lld bA %d bB %d rets %d %d pa %d pb %d nc0 %d boxA [%g %g %g %g] boxB [%g %g %g %g] thr %g %g\n",
+                                       w, step, bA, bB, rets[0], rets[1], pa, pb, nc0, boxA.xlo, boxA.xhi, boxA.ylo, boxA.yhi, boxB.xlo, boxB.xhi,
+                                       boxB.ylo, boxB.yhi, s.thr[bA], s.thr[bB]);
+#endif
+                            __syncwarp();
+                            if (slotp) *slotp = saved;         // put both bodies back: the general path runs this loop
+                            two_fail++;
+                            __syncwarp();
+                        }
+                    }
+                }
                 if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F && !(kp.mu > 0.0)) {   // (friction: general path only)
                     const int b = s.hi[0];
                     const long long before = ncalls_total;
@@ -1176,6 +1276,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             kp.status[w] = status;
             kp.steps[w] = step;
             kp.calls[w] += ncalls_total;
+            if (kp.general_calls) kp.general_calls[w] += ncalls_total - fast_calls;   // (introspection: which worlds cost time)
             kp.vflag[w] = verts_explicit ? 1 : 0;
             // hint for the next chunk: 0 quiescent (lean thread-per-world kernel), 1 candidates but no contact (prover
             // variant, when enabled), 2 contact phase (stay here)

@@ -856,6 +856,12 @@ int fizz_set_trace(FizzGroup *g, void *dev_records, int64_t capacity, void *dev_
     return FIZZ_OK;
 }
 
+int fizz_set_world_stats(FizzGroup *g, void *dev_general_calls) {
+    if (!g) return fail(FIZZ_E_ARG, "fizz_set_world_stats: null group");
+    g->kp.general_calls = (long long *)dev_general_calls;
+    return FIZZ_OK;
+}
+
 int fizz_kernel_info(FizzGroup *g, int32_t which, int32_t *regs, int32_t *smem, int32_t *threads, int32_t *blocks_per_sm,
                      int64_t *launches) {
     if (!g) return fail(FIZZ_E_ARG, "fizz_kernel_info: null group");

@@ -61,6 +61,7 @@ EXPORTS = {
     "fizz_step_logged": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "fizz_download": (C.c_int, [C.c_void_p, dp, dp, dp, dp, dp, lp, lp, lp, C.c_void_p]),
     "fizz_set_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fizz_set_world_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fizz_kernel_info": (C.c_int, [C.c_void_p, C.c_int32, ip, ip, ip, ip, lp]),
     "fizz_set_tuning": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     "fizz_snapshot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

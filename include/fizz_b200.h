@@ -210,6 +210,11 @@ int fizz_download(FizzGroup *g, double *pos, double *vel, double *heat, double *
  * counter (both caller-owned); pass NULL to disable.  The counter may exceed capacity (overflow is dropped). */
 int fizz_set_trace(FizzGroup *g, void *dev_records, int64_t capacity, void *dev_counter);
 
+/* Optional per-world introspection: dev_general_calls = device int64 [n_worlds] (caller-owned, zeroed by the caller) that
+ * accumulates, per world, the check_collisions() calls the contact kernel made OUTSIDE its single-contact fast path -- the
+ * expensive ones; NULL switches it off.  (Which world bounds a pass?  tools/shard_probe.py) */
+int fizz_set_world_stats(FizzGroup *g, void *dev_general_calls);
+
 /* Introspection for bench/roofline reporting: `which` = FIZZ_KERNEL_*; launches = kernels launched so far. */
 int fizz_kernel_info(FizzGroup *g, int32_t which, int32_t *regs_per_thread, int32_t *smem_bytes_per_block,
                      int32_t *block_threads, int32_t *blocks_per_sm, int64_t *launches);

@@ -261,6 +261,35 @@ def test_trapped_worlds_vs_oracle(mode):
                 assert np.array_equal(bits(ow.verts()), bits(verts[w])), tag
 
 
+@pytest.mark.parametrize("mode", [("hybrid", 96), ("hybrid", 7), ("hybrid3", 32), ("hybrid_sync", 64)],
+                         ids=["hybrid96", "hybrid7", "hybrid3-32", "hybrid_sync64"])
+def test_two_trapped_bodies_vs_oracle(mode):
+    """Worlds of the 8-GPU population of BASELINE config 3 (524288 worlds, seed 20260003) that bound its slowest shards: TWO
+    squares trapped at once, each inside a fixed body (every check_collisions() of the resolve loop returns two tuples until
+    one is out) -- the contact kernel runs the two resolve loops one after the other in registers and validates the
+    decomposition on the trajectories' bounding boxes; two bodies inside the SAME fixed body (the validation fails: general
+    path); a free-free pair stuck together.  Bit for bit against the oracle, default and tight watchdog."""
+    worlds = [235581, 309402, 305392, 161573, 502740, 404382, 248613, 63739]
+    sc = fz.load_in(scene_file("RAMPWORLD_2TRIANGLES_5SQUARES"))
+    d = np.ascontiguousarray(fz.perturbation_deltas(20260003, 524288, sc.n_free)[worlds])
+    for mc, steps in ((4096, 1500), (100, 600)):
+        spec = GroupSpec.from_scene(sc, len(worlds), d, max_calls=mc)
+        bw = tune(fz.BatchedWorld([spec]), mode)
+        bw.step(steps // 3)
+        bw.step(steps - steps // 3)
+        com, verts, heat, st, sd, calls = bw.com(), bw.vertices(), bw.heat(), bw.status(), bw.steps_done(), bw.calls()
+        ows = [oracle_from_spec(spec, w) for w in range(len(worlds))]
+        orc.run_batch(ows, steps, os.cpu_count() or 1)
+        for w, ow in enumerate(ows):
+            tag = (mode, mc, worlds[w])
+            assert ow.steps_done() == sd[w] and ow.status() == st[w] and ow.total_calls() == calls[w], tag
+            assert np.array_equal(bits(ow.com()), bits(com[w])) and bits(ow.heat()) == bits(heat[w]), tag
+            if st[w] == 0:
+                assert np.array_equal(bits(ow.verts()), bits(verts[w])), tag
+        if mc == 4096:
+            assert calls[0] > 100 * steps // 2      # the two-body world is busy from early on
+
+
 def test_runner_mode_call_patterns():
     """Runner launches only exist inside fizz_step() calls of >= 128 timesteps and end with them: any split of a run
     into calls -- long ones that use runners, short ones that do not, a mix -- ends in the same bits as one call and as

@@ -8,7 +8,7 @@ from fizz2d_b200.batch import GroupSpec
 heavy = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "63739,12860,58248,44270,36291,36227,47547,29797").split(",")]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 sc = fz.load_in(fz.scenes.scene_path("RAMPWORLD_2TRIANGLES_5SQUARES"))
-d = fz.perturbation_deltas(20260003, 65536, sc.n_free)
+d = fz.perturbation_deltas(20260003, 65536 * 8, sc.n_free)
 for wi in heavy:
     bw = fz.BatchedWorld([GroupSpec.from_scene(sc, 1, np.ascontiguousarray(d[[wi]]))])
     bw.step(1); bw.upload(); bw.counters(); torch.cuda.synchronize()

@@ -6,7 +6,10 @@ sys.path.insert(0, ".")
 import fizz2d_b200 as fz
 chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 mode = sys.argv[2] if len(sys.argv) > 2 else "hybrid"
-bw = fz.BatchedWorld.from_in(fz.scenes.scene_path("RAMPWORLD_2TRIANGLES_5SQUARES"), n_worlds=65536, perturb=True, seed=20260003)
+rank, G = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (0, 1)
+import types, bench
+specs, ids = bench.build_specs(types.SimpleNamespace(config=3, worlds=65536, max_calls=4096), rank, G)
+bw = fz.BatchedWorld(specs, ids)
 bw.set_tuning(mode, chunk)
 snap = bw.snapshot()
 for rep in range(3):
