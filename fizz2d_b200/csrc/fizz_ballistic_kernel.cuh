@@ -210,7 +210,7 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
 #pragma unroll
                 for (int j = i + 1; j < F; j++) {
                     const double dx = px[i] - px[j], dy = py[i] - py[j];
-                    const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                    const int sh = __double2hiint(sq2(dx, dy));
                     any |= !(sh > max(thr_h[i], thr_h[j]));
                 }
             }
@@ -221,7 +221,7 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
 #pragma unroll
                     for (int i = 0; i < F; i++) {
                         const double dx = px[i] - cx, dy = py[i] - cy;
-                        const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                        const int sh = __double2hiint(sq2(dx, dy));
                         any |= !(sh > max(thr_h[i], fh));
                     }
                 }
@@ -268,7 +268,7 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
     #pragma unroll
                 for (int j = i + 1; j < F; j++) {
                     const double dx = px[i] - px[j], dy = py[i] - py[j];
-                    const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                    const int sh = __double2hiint(sq2(dx, dy));
                     m |= (sh > max(thr_h[i], thr_h[j])) ? 0u : (1u << (j - i - 1));
                 }
                 cand[i] = m;
@@ -279,7 +279,7 @@ ballistic_kernel(const __grid_constant__ KParams kp, const long long *__restrict
     #pragma unroll
                 for (int i = 0; i < F; i++) {
                     const double dx = px[i] - cx, dy = py[i] - cy;
-                    const int sh = __double2hiint(fma(dy, dy, dx * dx));
+                    const int sh = __double2hiint(sq2(dx, dy));
                     cand[i] |= (sh > max(thr_h[i], fh)) ? 0u : (1u << (F - i - 1 + j));
                 }
             }

@@ -92,7 +92,7 @@ __device__ __forceinline__ ContactSmem contact_carve(double *base, int V, int FV
 
 // (ax, ay) / norm((ax, ay)) (:790): sqrt + two divisions, ~150 instructions with their slow paths -- ONE copy, out of line.
 __device__ __noinline__ double2 unit_normal(double ax, double ay) {
-    const double nrm = sqrt(fma(ay, ay, ax * ax));
+    const double nrm = sqrt(sq2(ax, ay));
     return make_double2(ax / nrm, ay / nrm);
 }
 
@@ -301,7 +301,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
     bool surv = false;
     {
         const double dx = cpx - ox, dy = cpy - oy;
-        const double d2 = fma(dy, dy, dx * dx);
+        const double d2 = sq2(dx, dy);
         surv = partner && !(d2 > thr_b && d2 > ot);
     }
     const unsigned mask0 = __ballot_sync(FULL, surv);
@@ -414,7 +414,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
             // ---- rest of the previous resolution, free body vs fixed body (:180-198) ------------------------------
             // :180-181 norm(nv) > VIBRATE_TOL.  The latency-tuned variant only applies pushes that are certainly longer
             // (see gate_min below): no test here
-            if (MULTI || fma(pnvy, pnvy, pnvx * pnvx) > vthr_r) { cpx += pnvx; cpy += pnvy; }
+            if (MULTI || sq2(pnvx, pnvy) > vthr_r) { cpx += pnvx; cpy += pnvy; }
             if constexpr (TRACK) {
                 bxlo = (cpx < bxlo) ? cpx : bxlo; bxhi = (cpx > bxhi) ? cpx : bxhi;
                 bylo = (cpy < bylo) ? cpy : bylo; byhi = (cpy > byhi) ? cpy : byhi;
@@ -432,7 +432,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
         const bool one_live = __popc(liveb) == 8;
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
         const double dx = cpx - ox, dy = cpy - oy;
-        const double d2 = fma(dy, dy, dx * dx);
+        const double d2 = sq2(dx, dy);
         const bool surv_l = !(d2 > tmax);
         // ---- memo check: edge k of b is (p2.y - p1.y, p1.x - p2.x) (:788-789) ----------------------------------------
         // (surv_l / miss_l stay local: kept alive across the loop they would be computed twice per pass; the code after
@@ -555,7 +555,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
         if (memo_stale()) continue;
         {   // the broad phase the last check() saw (same registers, same arithmetic)
             const double dx = cpx - ox, dy = cpy - oy;
-            const double d2 = fma(dy, dy, dx * dx);
+            const double d2 = sq2(dx, dy);
             surv = !(d2 > tmax);
         }
         // The check that ended the loop, when it saw the same candidates and a separating axis for every one of them, IS
@@ -618,7 +618,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
                     if (j < F) { qx = s.sx[j]; qy = s.sy[j]; qt = s.thr[j]; }
                     else { qx = s.fcx[j - F]; qy = s.fcy[j - F]; qt = s.fthr[j - F]; }
                     const double dx = s.sx[i] - qx, dy = s.sy[i] - qy;
-                    const double d2 = fma(dy, dy, dx * dx);
+                    const double d2 = sq2(dx, dy);
                     if (!(d2 > s.thr[i] && d2 > qt)) {
                         if (i == b && j >= F) pm |= 1u << j; else other = true;
                     }
@@ -807,7 +807,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         if (j < F) { ox = s.sx[j]; oy = s.sy[j]; ot = s.thr[j]; }
                         else { ox = s.fcx[j - F]; oy = s.fcy[j - F]; ot = s.fthr[j - F]; }
                         const double dx = s.sx[i] - ox, dy = s.sy[i] - oy;
-                        const double d2 = fma(dy, dy, dx * dx);
+                        const double d2 = sq2(dx, dy);
                         surv = !(d2 > s.thr[i] && d2 > ot);
                     }
                     const unsigned b = __ballot_sync(FULL, surv);
@@ -1057,7 +1057,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     const int n1 = kp.nv[ii], v1 = kp.vs[ii];
                     if (jj >= F) {                             // :171-198 free body vs fixed body
                         if (lane < n1) { s.vert[2 * (v1 + lane)] += nvx; s.vert[2 * (v1 + lane) + 1] += nvy; }  // :174
-                        const bool gate = fma(nvy, nvy, nvx * nvx) > kp.vib_thr;  // :180 norm(nv) > VIBRATE_TOL
+                        const bool gate = sq2(nvx, nvy) > kp.vib_thr;  // :180 norm(nv) > VIBRATE_TOL
                         double cpx = s.px[ii], cpy = s.py[ii], cvx = s.vx[ii], cvy = s.vy[ii];
                         const double m1 = s.mass[ii];
                         if (gate) { cpx += nvx; cpy += nvy; }                           // :181

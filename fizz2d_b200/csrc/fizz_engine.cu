@@ -40,7 +40,7 @@ __global__ void energy_kernel(const double *pos, const double *vel, const double
     for (int b = 0; b < F; b++) {
         const double m = mass[b * Wp + w];
         const double vx = vel[(2 * b) * Wp + w], vy = vel[(2 * b + 1) * Wp + w];
-        const double nv = sqrt(fma(vy, vy, vx * vx));
+        const double nv = sqrt(sq2(vx, vy));
         K += (.5 * m) * (nv * nv);
         P += (gy * m) * (height - pos[(2 * b + 1) * Wp + w]);
     }
@@ -225,13 +225,14 @@ static cudaEvent_t next_event(FizzGroup *g, cudaStream_t st) {
 extern "C" {
 
 int fizz_abi_version(void) { return FIZZ_ABI_VERSION; }
+int fizz_dot_mode(void) { return FIZZ_DOT_MODE; }
 const char *fizz_last_error(void) { return g_err.c_str(); }
 
 void fizz_host_norm2(int64_t n, const double *x, const double *y, double *out) {
-    for (int64_t i = 0; i < n; i++) out[i] = std::sqrt(std::fma(y[i], y[i], x[i] * x[i]));
+    for (int64_t i = 0; i < n; i++) out[i] = std::sqrt(sq2(x[i], y[i]));
 }
 void fizz_host_dot2(int64_t n, const double *a0, const double *a1, const double *b0, const double *b1, double *out) {
-    for (int64_t i = 0; i < n; i++) out[i] = std::fma(a1[i], b1[i], a0[i] * b0[i]);
+    for (int64_t i = 0; i < n; i++) out[i] = dot2(a0[i], a1[i], b0[i], b1[i]);
 }
 void fizz_host_sqrt_threshold(int64_t n, const double *r, double *out) {
     for (int64_t i = 0; i < n; i++) {
@@ -358,12 +359,12 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
             const int k2 = (k + 1 == n) ? 0 : k + 1;
             const double ax = xy[2 * k2 + 1] - xy[2 * k + 1];
             const double ay = xy[2 * k] - xy[2 * k2];
-            const double nrm = std::sqrt(std::fma(ay, ay, ax * ax));
+            const double nrm = std::sqrt(sq2(ax, ay));
             const double nx = ax / nrm, ny = ay / nrm;
             double lo, hi;
-            lo = hi = std::fma(ny, xy[1], nx * xy[0]);
+            lo = hi = dot2(nx, ny, xy[0], xy[1]);
             for (int v = 1; v < n; v++) {
-                const double cur = std::fma(ny, xy[2 * v + 1], nx * xy[2 * v]);
+                const double cur = dot2(nx, ny, xy[2 * v], xy[2 * v + 1]);
                 if (cur < lo) lo = cur;
                 if (cur > hi) hi = cur;
             }

@@ -36,7 +36,7 @@ __device__ __forceinline__ bool sat_pair(const T *sv, const T *sfix, const int *
             const int k2 = (k + 1 == n1) ? 0 : k + 1;
             const T ax = SV(v1 + k2, 1) - SV(v1 + k, 1);  // :775  (p2.y - p1.y, p1.x - p2.x)
             const T ay = SV(v1 + k, 0) - SV(v1 + k2, 0);
-            const T nrm = sqrt(fma(ay, ay, ax * ax));     // :790
+            const T nrm = sqrt(sq2(ax, ay));     // :790
             nx = ax / nrm; ny = ay / nrm;
         } else if (fx2) {
             const T *g = sfix + (v2 + (k - n1)) * 6;
@@ -47,7 +47,7 @@ __device__ __forceinline__ bool sat_pair(const T *sv, const T *sfix, const int *
             const int e2 = (e + 1 == n2) ? 0 : e + 1;
             const T ax = SV(v2 + e2, 1) - SV(v2 + e, 1);  // :778
             const T ay = SV(v2 + e, 0) - SV(v2 + e2, 0);
-            const T nrm = sqrt(fma(ay, ay, ax * ax));
+            const T nrm = sqrt(sq2(ax, ay));
             nx = ax / nrm; ny = ay / nrm;
         }
         T lo1, hi1;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int j = i + 1; j < F; j++) {
                     const T dx = sx[i] - sx[j], dy = sy[i] - sy[j];
-                    const T s = fma(dy, dy, dx * dx);
+                    const T s = sq2(dx, dy);
                     if (!(s > thr[i] && s > thr[j])) m |= 1u << (j - i - 1);
                 }
                 mask[i] = m;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < F; i++) {
                     const T dx = sx[i] - cx, dy = sy[i] - cy;
-                    const T s = fma(dy, dy, dx * dx);
+                    const T s = sq2(dx, dy);
                     if (!(s > thr[i] && s > ft)) mask[i] |= 1u << (F - i - 1 + j);
                 }
             }
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
                 const int n1 = stab[ii], v1 = stab[32 + ii];
                 if (jj >= F) {                             // :171-198 free body vs fixed body
                     for (int v = 0; v < n1; v++) { SV(v1 + v, 0) += nvx; SV(v1 + v, 1) += nvy; }  // :174
-                    const bool gate = sqrt(fma(nvy, nvy, nvx * nvx)) > c_vib_tol;               // :180
+                    const bool gate = sqrt(sq2(nvx, nvy)) > c_vib_tol;               // :180
                     const T m1 = kp.mass[ii * Wp + w];
 #pragma unroll
                     for (int b = 0; b < F; b++) {

@@ -47,6 +47,7 @@ class FizzContact(C.Structure):
 EXPORTS = {
     # name: (restype, argtypes)
     "fizz_abi_version": (C.c_int, []),
+    "fizz_dot_mode": (C.c_int, []),
     "fizz_last_error": (C.c_char_p, []),
     "fizz_host_norm2": (None, [C.c_int64, dp, dp, dp]),
     "fizz_host_dot2": (None, [C.c_int64, dp, dp, dp, dp, dp]),
@@ -79,26 +80,66 @@ EXPORTS = {
 RASTER_MAX_POLYGONS = 64
 
 _lib = None
+_dot_mode = None
 
 
 class FizzError(RuntimeError):
     pass
 
 
+def numpy_dot_mode(trials=2000, seed=12345):
+    """Which 2-vector dot/norm contract does THIS host's numpy/BLAS follow?  1: fma(a1,b1,a0*b0) -- the golden
+    host's --, 2: fma(a0,b0,a1*b1), 0: unfused.  Exact integer arithmetic on the operands decides (no libm, no GPU)."""
+    import numpy as np
+    from fractions import Fraction
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((trials, 4)) * np.exp(rng.uniform(-3, 3, (trials, 4)))
+    alive = {0, 1, 2}
+
+    def rn(fr):                                       # Fraction -> nearest double (ties to even): float() does that
+        return float(fr)
+    for a0, a1, b0, b1 in v:
+        got = float(np.dot(np.array([a0, a1]), np.array([b0, b1])))
+        A0, A1, B0, B1 = (Fraction(float(x)) for x in (a0, a1, b0, b1))
+        want = {1: rn(A1 * B1 + Fraction(rn(A0 * B0))), 2: rn(A0 * B0 + Fraction(rn(A1 * B1))),
+                0: rn(Fraction(rn(A0 * B0)) + Fraction(rn(A1 * B1)))}
+        alive = {m for m in alive if want[m] == got}
+        if not alive:
+            raise FizzError("this host's numpy 2-vector dot follows none of the three known contracts (SURVEY Q14)")
+    return 1 if 1 in alive else min(alive)
+
+
+def dot_mode():
+    """The contract the loaded library reproduces: $FIZZ_DOT_MODE if set, else what numpy does on this host."""
+    global _dot_mode
+    if _dot_mode is None:
+        env = os.environ.get("FIZZ_DOT_MODE")
+        _dot_mode = int(env) if env not in (None, "") else numpy_dot_mode()
+    return _dot_mode
+
+
 def load():
     """Load libfizz_b200.so (raises if it has not been built: run `python -m fizz2d_b200.build` or
-    `__graft_entry__.build()`)."""
+    `__graft_entry__.build()`).  On a host whose numpy fuses the 2-vector dot differently from the golden host, the
+    library of the matching FIZZ_DOT_MODE is loaded instead (built in-tree on first use: needs nvcc)."""
     global _lib
     if _lib is None:
-        if not os.path.isfile(LIB_PATH):
-            raise FizzError("CUDA extension %s is missing; build it with __graft_entry__.build()" % LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+        path = LIB_PATH
+        mode = dot_mode()
+        if mode != 1 and not os.environ.get("FIZZ_B200_LIB"):
+            from . import build as _build
+            path = _build.build_extension(dot_mode=mode)
+        if not os.path.isfile(path):
+            raise FizzError("CUDA extension %s is missing; build it with __graft_entry__.build()" % path)
+        L = C.CDLL(path)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
         if L.fizz_abi_version() != 2:
             raise FizzError("ABI version mismatch")
+        if L.fizz_dot_mode() != mode and not os.environ.get("FIZZ_B200_LIB"):
+            raise FizzError("library %s was built for dot mode %d, this host needs %d" % (path, L.fizz_dot_mode(), mode))
         _lib = L
     return _lib
 

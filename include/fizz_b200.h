@@ -140,6 +140,10 @@ typedef struct FizzContact {
 } FizzContact;
 
 int fizz_abi_version(void);
+/* The numpy 2-vector dot/norm contract this build of the library reproduces (csrc/fizz_common.cuh):
+ * 1 = fma(a1, b1, a0*b0) (default: the golden host's OpenBLAS), 2 = fma(a0, b0, a1*b1), 0 = unfused.  One library per
+ * mode (libfizz_b200.so, libfizz_b200_dot0.so, libfizz_b200_dot2.so); the Python loader picks by probing numpy. */
+int fizz_dot_mode(void);
 const char *fizz_last_error(void);
 
 /* Host helpers implementing numpy's 2-vector contract for the Python loader's init-time math:

@@ -48,8 +48,22 @@ typedef struct {
     double nx, ny, mag;
 } hit;
 
-static inline double dot2(double a0, double a1, double b0, double b1) { return fma(a1, b1, a0 * b0); }
-static inline double norm2(double a0, double a1) { return sqrt(fma(a1, a1, a0 * a0)); }
+/* np.dot / np.linalg.norm of 2-vectors as the host's numpy evaluates them: host-dependent, hence a
+ * build-time switch (make FZO_DOT_MODE=0|1|2 -> libfizz_oracle_dot<m>.so); 1 is the golden host's contract. */
+#ifndef FZO_DOT_MODE
+#define FZO_DOT_MODE 1
+#endif
+static inline double dot2(double a0, double a1, double b0, double b1) {
+#if FZO_DOT_MODE == 1
+    return fma(a1, b1, a0 * b0);
+#elif FZO_DOT_MODE == 2
+    return fma(a0, b0, a1 * b1);
+#else
+    return a0 * b0 + a1 * b1;
+#endif
+}
+static inline double norm2(double a0, double a1) { return sqrt(dot2(a0, a1, a0, a1)); }
+int fzo_dot_mode(void) { return FZO_DOT_MODE; }
 
 fzo_world *fzo_create(int nfree, int nfixed, const int *nverts, const double *com, const double *vel,
                       const double *radius, const double *mass, const double *offx, const double *offy,

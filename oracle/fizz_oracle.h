@@ -77,6 +77,9 @@ double fzo_total_ops(const fzo_world *w);  /* algorithmic FP64 ops (SURVEY 8d ru
 void fzo_trace(fzo_world *w, fzo_contact *buf, long cap);
 long fzo_contact_count(const fzo_world *w);
 
+/* The numpy 2-vector dot/norm contract this build follows: 1 = fma(a1,b1,a0*b0) (default), 2, 0. */
+int fzo_dot_mode(void);
+
 /* Batch helper for the CPU baseline: step `n` worlds `nsteps` each on `nthreads` pthreads. */
 void fzo_run_batch(fzo_world **worlds, long n, long nsteps, int nthreads);
 

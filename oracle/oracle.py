@@ -19,7 +19,9 @@ import numpy as np
 from numpy.linalg import norm
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfizz_oracle.so")
+# numpy's 2-vector dot/norm contract the oracle is built for: $FZO_DOT_MODE (0, 1 = default, 2)
+DOT_MODE = int(os.environ.get("FZO_DOT_MODE", "1") or 1)
+LIB_PATH = os.path.join(HERE, "libfizz_oracle.so" if DOT_MODE == 1 else "libfizz_oracle_dot%d.so" % DOT_MODE)
 
 DEFAULT_PARAMS = dict(ELASTICITY=1.0, EPSILON=1e-12, TIME_TOL=1e-10, COLLISION_TOL=.1, VIBRATE_TOL=1e-5)
 TIME_DISC = .05
@@ -28,7 +30,7 @@ TIME_DISC = .05
 def build(force=False):
     if force or not os.path.isfile(LIB_PATH) or \
             os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "fizz_oracle.c")):
-        subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []))
+        subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []) + ([] if DOT_MODE == 1 else ["dotmodes"]))
     return LIB_PATH
 
 
@@ -175,6 +177,7 @@ def lib():
         L.fzo_calls_last_step.argtypes = [C.c_void_p]; L.fzo_calls_last_step.restype = C.c_long
         L.fzo_total_calls.argtypes = [C.c_void_p]; L.fzo_total_calls.restype = C.c_long
         L.fzo_total_ops.argtypes = [C.c_void_p]; L.fzo_total_ops.restype = C.c_double
+        L.fzo_dot_mode.restype = C.c_int
         L.fzo_trace.argtypes = [C.c_void_p, C.POINTER(_Contact), C.c_long]
         L.fzo_contact_count.argtypes = [C.c_void_p]; L.fzo_contact_count.restype = C.c_long
         L.fzo_run_batch.argtypes = [C.POINTER(C.c_void_p), C.c_long, C.c_long, C.c_int]
