@@ -26,7 +26,8 @@ def needs_build(dot_mode=1):
         return True
     t = os.path.getmtime(out)
     import glob
-    deps = SRC + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + [os.path.join(ROOT, "include", "fizz_b200.h")]
+    deps = SRC + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "*.inc")) + \
+        [os.path.join(ROOT, "include", "fizz_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

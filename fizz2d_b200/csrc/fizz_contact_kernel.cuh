@@ -115,135 +115,16 @@ __device__ __forceinline__ void edge_normal(const ContactSmem &s, int m, double 
     }
 }
 
-// One SAT axis of polypoly_collision (:787-830) for the packed pair `m` (ii free, jj free-or-fixed): axis index
-// k in [0, n1+n2) in reference order (poly1's edges, then poly2's), vertices read from the warp's explicit
-// vertex array.  Returns the overlap on this axis and whether the axis separates the polygons.
-// FLOOR = true: returns instead, in `cur`, min(hi2 - lo1, hi1 - lo2) of the intervals BEFORE the role swap of :815 -- a lower
-// bound of the overlap the axis reports whichever polygon ends up as "the first" (used by the trial-search shortcut).
-template <bool FLOOR = false>
-__device__ __forceinline__ void sat_axis(const ContactSmem &s, int F, pairmeta_t m, int k, double &nx, double &ny,
-                                         double &cur, bool &sep) {
-    const int jj = PM_JJ(m), n1 = PM_N1(m), n2 = PM_N2(m), v1 = PM_V1(m), v2 = PM_V2(m);
-    const bool fx2 = jj >= F;
-    const double *vert = s.vert;
-    double lo2 = 0.0, hi2 = 0.0;
-    bool own2 = false;
-    FIZZ_ASSERT(k >= 0 && k < n1 + n2 && n1 >= 3 && n2 >= 3 && PM_II(m) < F);
-    if (k < n1) {
-        const int k2 = (k + 1 == n1) ? 0 : k + 1;
-        edge_normal<true>(s, v1 + k, vert[2 * (v1 + k)], vert[2 * (v1 + k) + 1], vert[2 * (v1 + k2)],
-                          vert[2 * (v1 + k2) + 1], nx, ny);
-    } else if (fx2) {
-        const double *g = s.sfix + (v2 + (k - n1)) * 6;  // precomputed, bit-identical to :778,:790,:806-811
-        nx = g[2]; ny = g[3]; lo2 = g[4]; hi2 = g[5];
-        own2 = true;
-    } else {
-        const int e = k - n1;
-        const int e2 = (e + 1 == n2) ? 0 : e + 1;
-        edge_normal<true>(s, v2 + e, vert[2 * (v2 + e)], vert[2 * (v2 + e) + 1], vert[2 * (v2 + e2)],
-                          vert[2 * (v2 + e2) + 1], nx, ny);
-    }
-    double lo1, hi1;
-    lo1 = hi1 = dot2(nx, ny, vert[2 * v1], vert[2 * v1 + 1]);                // :795
-    for (int v = 1; v < n1; v++) {                                           // :799-804
-        const double c = dot2(nx, ny, vert[2 * (v1 + v)], vert[2 * (v1 + v) + 1]);
-        if (c < lo1) lo1 = c;
-        if (c > hi1) hi1 = c;
-    }
-    if (!own2) {
-        if (fx2) {
-            const double *g = s.sfix + v2 * 6;
-            lo2 = hi2 = dot2(nx, ny, g[0], g[1]);                            // :796
-            for (int v = 1; v < n2; v++) {                                   // :806-811
-                const double c = dot2(nx, ny, g[v * 6], g[v * 6 + 1]);
-                if (c < lo2) lo2 = c;
-                if (c > hi2) hi2 = c;
-            }
-        } else {
-            lo2 = hi2 = dot2(nx, ny, vert[2 * v2], vert[2 * v2 + 1]);
-            for (int v = 1; v < n2; v++) {
-                const double c = dot2(nx, ny, vert[2 * (v2 + v)], vert[2 * (v2 + v) + 1]);
-                if (c < lo2) lo2 = c;
-                if (c > hi2) hi2 = c;
-            }
-        }
-    }
-    if (FLOOR) {
-        const double a = hi2 - lo1, b = hi1 - lo2;
-        cur = (a < b) ? a : b;
-        sep = false;
-        return;
-    }
-    if (lo1 > lo2) {                                                         // :815-817
-        double t = lo1; lo1 = lo2; lo2 = t;
-        t = hi1; hi1 = hi2; hi2 = t;
-    }
-    sep = hi1 < lo2;                                                         // :820
-    cur = hi1 - lo2;                                                         // :824
-}
-
-// Whole polypoly_collision for one pair evaluated by ONE lane with the free vertices rebuilt on the fly from a
-// trial's moved centres of mass (speculative halving).  Returns true and |overlap| when the pair collides.
-__device__ __forceinline__ bool sat_pair_trial(const ContactSmem &s, int F, pairmeta_t m, double c1x, double c1y,
-                                               double c2x, double c2y, double &mag) {
-    const int jj = PM_JJ(m), n1 = PM_N1(m), n2 = PM_N2(m), v1 = PM_V1(m), v2 = PM_V2(m);
-    const bool fx2 = jj >= F;
-    const double *off = s.off;
-    double overlap = INFINITY;
-    bool have = false;
-    for (int k = 0; k < n1 + n2; k++) {
-        double nx, ny, lo2 = 0.0, hi2 = 0.0;
-        bool own2 = false;
-        if (k < n1) {
-            const int k2 = (k + 1 == n1) ? 0 : k + 1;
-            edge_normal<false>(s, v1 + k, off[2 * (v1 + k)] + c1x, off[2 * (v1 + k) + 1] + c1y, off[2 * (v1 + k2)] + c1x,
-                               off[2 * (v1 + k2) + 1] + c1y, nx, ny);
-        } else if (fx2) {
-            const double *g = s.sfix + (v2 + (k - n1)) * 6;
-            nx = g[2]; ny = g[3]; lo2 = g[4]; hi2 = g[5];
-            own2 = true;
-        } else {
-            const int e = k - n1;
-            const int e2 = (e + 1 == n2) ? 0 : e + 1;
-            edge_normal<false>(s, v2 + e, off[2 * (v2 + e)] + c2x, off[2 * (v2 + e) + 1] + c2y, off[2 * (v2 + e2)] + c2x,
-                               off[2 * (v2 + e2) + 1] + c2y, nx, ny);
-        }
-        double lo1, hi1;
-        lo1 = hi1 = dot2(nx, ny, off[2 * v1] + c1x, off[2 * v1 + 1] + c1y);
-        for (int v = 1; v < n1; v++) {
-            const double c = dot2(nx, ny, off[2 * (v1 + v)] + c1x, off[2 * (v1 + v) + 1] + c1y);
-            if (c < lo1) lo1 = c;
-            if (c > hi1) hi1 = c;
-        }
-        if (!own2) {
-            if (fx2) {
-                const double *g = s.sfix + v2 * 6;
-                lo2 = hi2 = dot2(nx, ny, g[0], g[1]);
-                for (int v = 1; v < n2; v++) {
-                    const double c = dot2(nx, ny, g[v * 6], g[v * 6 + 1]);
-                    if (c < lo2) lo2 = c;
-                    if (c > hi2) hi2 = c;
-                }
-            } else {
-                lo2 = hi2 = dot2(nx, ny, off[2 * v2] + c2x, off[2 * v2 + 1] + c2y);
-                for (int v = 1; v < n2; v++) {
-                    const double c = dot2(nx, ny, off[2 * (v2 + v)] + c2x, off[2 * (v2 + v) + 1] + c2y);
-                    if (c < lo2) lo2 = c;
-                    if (c > hi2) hi2 = c;
-                }
-            }
-        }
-        if (lo1 > lo2) {
-            double t = lo1; lo1 = lo2; lo2 = t;
-            t = hi1; hi1 = hi2; hi2 = t;
-        }
-        if (hi1 < lo2) return false;
-        const double cur = hi1 - lo2;
-        if (cur < overlap) { overlap = cur; have = true; }
-    }
-    mag = fabs(overlap);
-    return have;
-}
+#define FIZZ_SAT_NAME(n) n
+#define FIZZ_SAT_UNROLL
+#include "fizz_sat.inc"
+#undef FIZZ_SAT_NAME
+#undef FIZZ_SAT_UNROLL
+#define FIZZ_SAT_NAME(n) n##_compact
+#define FIZZ_SAT_UNROLL _Pragma("unroll 1")
+#include "fizz_sat.inc"
+#undef FIZZ_SAT_NAME
+#undef FIZZ_SAT_UNROLL
 
 // ---------------------------------------------------------------------------------------------------------------
 // Single-contact fast path: the resolve loop AND, while the pattern holds, whole timesteps, in registers.
@@ -847,7 +728,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                             mb = s.sp[pb];
                             actb = my_k < PM_N1(mb) + PM_N2(mb);
                         }
-                        if (acta) sat_axis(s, F, ma, my_k, nxa, nya, cura, sepa);
+                        if (acta) sat_axis(s, F, ma, my_k, nxa, nya, cura, sepa);   // (FAST only)
                         if (actb) sat_axis(s, F, mb, my_k, nxb, nyb, curb, sepb);
     #pragma unroll
                         for (int set = 0; set < 2; set++) {
@@ -906,7 +787,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                             m = s.sp[pa];
                             act = my_k < PM_N1(m) + PM_N2(m);
                         }
-                        if (act) sat_axis(s, F, m, my_k, nx, ny, cur, sep);
+                        if (act) sat_axis_compact(s, F, m, my_k, nx, ny, cur, sep);   // (!FAST only)
                         const unsigned sepbits = __ballot_sync(FULL, sep);
                         const bool pair_sep = (sepbits & slot_mask) != 0;
                         const bool valid = act && (cur < INFINITY);
@@ -1011,7 +892,10 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                                                     c2x, c2y, dvx, dvy);
                                 }
                                 double mag;
-                                if (sat_pair_trial(s, F, m, c1x, c1y, c2x, c2y, mag))
+                                bool hit_t;
+                                if constexpr (FAST) hit_t = sat_pair_trial(s, F, m, c1x, c1y, c2x, c2y, mag);
+                                else hit_t = sat_pair_trial_compact(s, F, m, c1x, c1y, c2x, c2y, mag);
+                                if (hit_t)
                                     if (mag > mo) mo = mag;
                             }
                             done_t = !(mo > kp.coll_tol && dtt > kp.time_tol);
