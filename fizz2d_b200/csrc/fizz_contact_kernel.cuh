@@ -151,6 +151,8 @@ __device__ __forceinline__ void edge_normal(const ContactSmem &s, int m, double 
 // ---------------------------------------------------------------------------------------------------------------
 enum { TRAP_MIDSTEP = 0, TRAP_EMPTY = 1, TRAP_BOUNDARY = 2 };
 
+// Lanes map to (candidate partner, SAT axis) items in slots of 8 lanes -- or 16 in scenes whose largest n1 + n2 exceeds 8
+// (kp.swl; e.g. a triangle against PENTAGONVOID's hexagon, the GA population of BASELINE config 5).
 // b has 3 or 4 vertices, kept in four register pairs: a triangle's first vertex (in the lane's rotation) sits there twice,
 // which changes neither a minimum nor a maximum of projections -- one instruction stream for both shapes (the kernel is
 // bound by instruction fetch wherever it is not bound by this chain).  MULTI = false: the variant of the throughput
@@ -187,9 +189,11 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
     }
     const unsigned mask0 = __ballot_sync(FULL, surv);
     const int ncand = __popc(mask0);
-    if (ncand == 0 || ncand > 4 || (mask0 & ((1u << F) - 1u)) != 0) return TRAP_MIDSTEP;  // only fixed partners, one 32-lane set
+    // slots of 8 lanes (up to 4 candidate partners) or, in scenes with a larger n1 + n2, of 16 lanes (up to 2)
+    const int swl = kp.swl, sw = 1 << swl;
+    if (ncand == 0 || ncand > (32 >> swl) || (mask0 & ((1u << F) - 1u)) != 0) return TRAP_MIDSTEP;  // only fixed partners, one 32-lane set
 
-    const int slot = lane >> 3, kk = lane & 7;
+    const int slot = lane >> swl, kk = lane & (sw - 1);
     int jj = -1;
     {
         unsigned mm = mask0;
@@ -201,7 +205,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
     const bool active = (jj >= 0) && (kk < n1 + n2);
     const bool freeaxis = active && (kk < n1);
     const bool active_slot = (jj >= 0);
-    const unsigned slot_bits = 0xffu << (8 * slot);
+    const unsigned slot_bits = ((1u << sw) - 1u) << (sw * slot);
     // b's vertices, all of them in every lane, ROTATED so that a lane that owns edge k of b finds the edge's end points
     // in registers 0 and 1 (min/max over the same set of projections: only the sign of a zero could depend on order).
     const int rot = freeaxis ? kk : 0;
@@ -308,9 +312,9 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
         }
         const bool m1_ = mine && hiw == mhi;
         const unsigned mlo = __reduce_min_sync(FULL, m1_ ? low : 0xffffffffu);
-        // exactly one candidate slot without a separating axis: its 8 lanes are the `mine` lanes
+        // exactly one candidate slot without a separating axis: its lanes are the `mine` lanes
         liveb = __ballot_sync(FULL, mine);
-        const bool one_live = __popc(liveb) == 8;
+        const bool one_live = __popc(liveb) == sw;
         // ---- broad phase of the pairs (b, *) on b's new snapshot (= com: finish_update follows every push) ----------
         const double dx = cpx - ox, dy = cpy - oy;
         const double d2 = sq2(dx, dy);
@@ -998,7 +1002,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     // trajectories; a failed check restores both bodies and the general path runs the loop).  The loop then
                     // makes max(n_A, n_B) checks.  Heat is added tuple by tuple in list order, which the two separate loops
                     // cannot reproduce: only taken when ELASTICITY == 1 (every term is +0; a non-finite one restores too).
-                    if (speculate && nh == 2 && SW == 8 && two_fail < 2 && s.hj[0] >= F && s.hj[1] >= F && s.hi[0] != s.hi[1] &&
+                    if (speculate && nh == 2 && SW <= 16 && two_fail < 2 && s.hj[0] >= F && s.hj[1] >= F && s.hi[0] != s.hi[1] &&
                         kp.ome2 == 0.0 && !(kp.mu > 0.0)) {
                         const int bA = s.hi[0], bB = s.hi[1];
                         const int nA = kp.nv[bA], nB = kp.nv[bB];
@@ -1078,7 +1082,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                         }
                     }
                 }
-                if (speculate && nh == 1 && SW == 8 && s.hj[0] >= F && !(kp.mu > 0.0)) {   // (friction: general path only)
+                if (speculate && nh == 1 && SW <= 16 && s.hj[0] >= F && !(kp.mu > 0.0)) {   // (friction: general path only)
                     const int b = s.hi[0];
                     const long long before = ncalls_total;
                     const int nb = kp.nv[b];

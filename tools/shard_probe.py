@@ -9,6 +9,10 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 config = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ranks = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(G))
 cfg = bench.CONFIGS[config]
+if cfg["kind"] == "ga":            # the population law is sequential: draw the whole population once, not once per shard
+    from fizz2d_b200 import ga
+    _pop = ga.random_convex_polygons(cfg["seed"], cfg["worlds"] * G)
+    ga.random_convex_polygons = lambda seed, n: _pop
 args = types.SimpleNamespace(config=config, worlds=cfg["worlds"], max_calls=4096)
 for r in ranks:
     specs, ids = bench.build_specs(args, r, G)
@@ -32,9 +36,10 @@ for r in ranks:
     print("rank %d/%d: pass %.1f ms | heaviest worlds (local idx, calls, steps done, status): %s | fast %.3f of %d contact calls" % (
         r, G, ts[-1], [(int(i), int(c[i]), int(sd[i]), int(st[i])) for i in o],
         sum(x["fast_path_calls"] for x in k) / max(1, sum(x["contact_calls"] for x in k)), sum(x["contact_calls"] for x in k)), flush=True)
-    gc = gstat[0].cpu().numpy()
-    og = np.argsort(-gc)[:5]
-    print("   most general-path calls (local idx, general calls, all calls, steps, status):",
-          [(int(i), int(gc[i]), int(c[bw.groups[0].world_ids[i]]), int(sd[bw.groups[0].world_ids[i]]), int(st[bw.groups[0].world_ids[i]])) for i in og])
+    for gi, g in enumerate(bw.groups):
+        gc = gstat[gi].cpu().numpy()
+        og = np.argsort(-gc)[:3]
+        print("   group %d (%s vertices): most general-path calls (local idx, general calls, all calls, steps, status):" % (gi, g.spec.nverts_free),
+              [(int(g.world_ids[i]), int(gc[i]), int(c[g.world_ids[i]]), int(sd[g.world_ids[i]]), int(st[g.world_ids[i]])) for i in og])
     bw.close()
     del bw
