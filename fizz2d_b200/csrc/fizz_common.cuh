@@ -46,6 +46,55 @@ struct KParams {
     int max_calls;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Time-parallel stepping of heavy worlds ("spec rounds"; fizz_spec.cuh, fizz_engine.cu: fizz_step).
+// A world is a sequential chain (update() t+1 needs the state update() t left), but the state a trapped world starts its
+// next timestep from is almost always PREDICTABLE without running the timestep: the trapped coordinate comes back to
+// the same value, everything else moved ballistically.  So K warps evaluate update() t, t+L, t+2L, ... of one world
+// side by side, warp k starting from the state predicted for timestep t + kL, and a commit step accepts the longest
+// prefix of slots whose START state equals, bit for bit, the END state of the slot before (slot 0 starts from the real
+// state).  An accepted slot ran the real update() on the real state, so its result is the reference's; a mispredicted
+// slot is thrown away and its timesteps are evaluated again in the next round.  Results never depend on the predictor.
+//
+// Slot record (doubles / 64-bit words), one per (list entry, slot), SPEC_K slots per list entry:
+//   [0, 4F)   start state: x, y, vx, vy of every free body      [4F, 8F) end state
+//   [8F + 0]  flags: bit 0 "ran", bit 1 "clean" (status 0, heat bit-identical to the world's, vertices derived)
+//   [8F + 1]  timesteps advanced   [8F + 2] check_collisions() made   [8F + 3] ... of those in the fast path
+//   [8F + 4]  check_collisions() of the last completed timestep        [8F + 5] heat   [8F + 6] status   [8F + 7] vflag
+//   [8F + 8]  cost of the last completed timestep (see the tier word)
+// Control record per WORLD (hints and statistics only; survives chunks and calls; a stale one costs a misprediction):
+//   [0] 2 = the classes below are a usable predictor   [1] [2] predictor class of every position coordinate (one byte
+//   each: 0 unchanged, 1 Point.move over TIME_DISC, 2 Point.move over the remainder of a timestep that fell back, 3
+//   unknown)   [3] consecutive rounds whose last accepted slot no move explains   [4] items of the current round that
+//   are finished (the last one commits)   statistics: [5] timesteps accepted  [6] timesteps evaluated  [7] rounds that
+//   accepted fewer slots than ran  [8] rounds without a predictor  [9] rounds
+struct SpecParams {
+    double *slots;
+    long long *ctrl;
+    int S;                      // timesteps per world and round (K L ~ S)
+    int D;                      // cost per item the slot length aims at: L = clamp(D / cost of a timestep, 1, 16)
+    int budget_cost;            // a world without a usable predictor: slot 0 alone, until it has cost this much
+    int budget_steps;           // ... or made this many timesteps, per round
+    int enabled;
+    int round;                  // (debug statistics only)
+    unsigned long long *dbg;    // optional [rounds][4]: longest item (cycles), sum, items, items given up
+};
+constexpr int SPEC_K = 32;          // slots per list entry (stride of the item index; a world uses K <= SPEC_K of them)
+constexpr int SPEC_CTRL_WORDS = 10;
+__host__ __device__ __forceinline__ int spec_slot_words(int F) { return 8 * F + 10; }
+// The tier word of a world: bits 0..7 scheduling tier, 8..31 check_collisions() of its last completed timestep, 32..55
+// COST of that timestep = the clock cycles the warp spent on it / 256 (about one call of the register-resident path).
+// Slot shape of a world for the spec rounds:
+__host__ __device__ __forceinline__ void spec_shape(long long tier_word, int S, int D, int &K, int &L) {
+    long long cost = (tier_word >> 32) & 0xffffff;
+    if (cost < 1) cost = 1;
+    long long l = D / cost;
+    L = (int)(l < 1 ? 1 : (l > 16 ? 16 : l));
+    K = (S + L - 1) / L;
+    if (K > SPEC_K) K = SPEC_K;
+    if (K < 2) K = 2;
+}
+
 // Debug builds (-DFIZZ_DEBUG): index checks that trap instead of corrupting memory (compute-sanitizer is closed on
 // the development pool).  Release builds compile them out.
 #ifdef FIZZ_DEBUG
@@ -106,5 +155,30 @@ __device__ __forceinline__ void trace_hit(const KParams &kp, long long w, long l
         ovx = vax_ + (accx) * halfdt_;                                               \
         ovy = vay_ + (accy) * halfdt_;                                               \
     }
+
+
+// One coordinate of Point.move: the operation sequence of FIZZ_MOVE_POINT (used by the predictor of the spec rounds).
+__host__ __device__ __forceinline__ void move_coord(double &p, double &v, double h, double a0, double acc) {
+    const double halfdt = .5 * h;
+    const double va = v + a0 * halfdt;
+    p = p + va * h;
+    v = va + acc * halfdt;
+}
+// One step of the predictor for one coordinate (class byte: see SpecParams).  Classes 0 and 3 leave it alone.
+__device__ __forceinline__ void spec_predict(double &p, double &v, int cls, double dt, double rdt, double acc) {
+    if (cls == 1) move_coord(p, v, dt, acc, acc);
+    else if (cls == 2) move_coord(p, v, rdt, acc, acc);
+}
+
+// The trial that ends the halving search of a timestep in which EVERY trial fails: dt / 2 / 2 ... (:106) is dt * 2^-t
+// exactly as long as nothing gets subnormal; the first t >= 1 with dt_t <= TIME_TOL (:99).  Warp-wide; kstar < 0: none.
+__device__ __forceinline__ void halving_floor(const KParams &kp, int lane, int &kstar, double &dtk) {
+    double dtt = kp.time_disc;
+    if (dtt > 1e-280) dtt = dtt * __longlong_as_double((long long)(1023 - lane) << 52);
+    else for (int t = 0; t < lane; t++) dtt = dtt / 2;
+    const unsigned doneb = __ballot_sync(0xffffffffu, lane >= 1 && !(dtt > kp.time_tol));
+    kstar = __ffs(doneb) - 1;
+    dtk = __shfl_sync(0xffffffffu, dtt, kstar < 0 ? 0 : kstar);
+}
 
 }  // namespace fizz

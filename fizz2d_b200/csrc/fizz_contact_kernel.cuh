@@ -25,12 +25,18 @@
 
 #include "fizz_common.cuh"
 #include "fizz_ext.cuh"
+#include "fizz_spec.cuh"
 
 namespace fizz {
 
 constexpr int CONTACT_WARPS = 4;  // warps per CTA
 constexpr int CONTACT_BLOCK = CONTACT_WARPS * 32;
+#ifdef FIZZ_RUNNER_DEBUG
+__device__ unsigned long long g_dbg_cycles[65536];   // per world: cycles in ordinary (non-spec) items from timestep 2688 on
+#endif
 constexpr int SP_CAP = 160;       // survivor list capacity (>= MAX_PAIRS)
+constexpr unsigned long long BULK_LIST = 16384;  // work lists this long are a throughput phase: the compact instance takes them
+constexpr long long FIZZ_ST_SPEC_ABORT = 100;    // internal: a spec item gave up (never leaves its slot record)
 
 // packed pair descriptor: ii[0,4) jj[4,9) n1[9,14) n2[14,19) v1[19,27) v2[27,35)
 typedef unsigned long long pairmeta_t;
@@ -164,7 +170,10 @@ template <bool MULTI, bool TRACK = false>
 __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &kp, int F, int X, int lane, int b,
                                            double &heat, int &ncalls, long long &ncalls_total, long long &step, int &k,
                                            double &dt, int &steps_here, int &last_calls, const int kstar, const double dtk,
+                                           const long long target, const long long stop_at, const long long abort_at,
                                            TrapBox *box = nullptr) {
+    // (spec rounds: stop_at / abort_at are values of ncalls_total -- every call made here costs one unit -- at which the
+    //  item ends at the next timestep boundary / gives the resolve loop back to the general path, which aborts the item)
     constexpr int NM = 4;
     const unsigned FULL = 0xffffffffu;
     const int n1 = kp.nv[b];
@@ -229,7 +238,11 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
         anx = g[2]; any_ = g[3]; alo2 = g[4]; ahi2 = g[5];
     }
     int passes = 0;
-    int budget = kp.max_calls - ncalls;  // watchdog: the general path raises FIZZ_ST_CAPPED
+    auto capped_budget = [&]() -> int {
+        const long long wd = kp.max_calls - ncalls, left = abort_at - ncalls_total;
+        return (int)(left < wd ? (left < 0 ? 0 : left) : wd);
+    };
+    int budget = capped_budget();  // watchdog: the general path raises FIZZ_ST_CAPPED
     // (a "travel budget" that skips the broad phase while b cannot have reached a partner's threshold was measured and
     //  dropped: trapped bodies jump 20-100 px per pass, the budget is exhausted almost every pass)
     //
@@ -423,7 +436,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
             k = kstar; dt = dtk;
             ncalls = kstar + 2;                                             // trials 0 .. kstar and the fallback's check
             ncalls_total += kstar + 2;
-            budget = kp.max_calls - ncalls;
+            budget = capped_budget();
             passes = -1;
             in_prologue_step = true;
             phase = PH_RESOLVE;
@@ -488,7 +501,7 @@ __device__ __forceinline__ int trapped_run(const ContactSmem &s, const KParams &
             in_prologue_step = false;
             ret = TRAP_BOUNDARY;
         }
-        if (step >= kp.target_steps) break;
+        if (step >= target || ncalls_total >= stop_at) break;
         {
             // broad phase of ALL pairs on the snapshots (:272-281): exactly the fixed partners of b, nothing else
             unsigned pm = 0u;
@@ -573,7 +586,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(CONTACT_BLOCK, FAST ? FIZZ_FAST_CTAS : FIZZ_GEN_CTAS)
 contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__ list,
                const unsigned long long *__restrict__ count_ptr, unsigned long long *cursor,
-               unsigned long long count_cap = ~0ull, int runner = 0) {
+               unsigned long long count_cap, int runner, const __grid_constant__ SpecParams sp) {
     extern __shared__ double smem_c[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -606,44 +619,126 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
     // exactly as long as nothing gets subnormal; the first t >= 1 with dt_t <= TIME_TOL (:99).  (for trapped_run)
     int kstar_all;
     double dtk_all;
-    {
-        double dtt = kp.time_disc;
-        if (dtt > 1e-280) dtt = dtt * __longlong_as_double((long long)(1023 - lane) << 52);
-        else for (int t = 0; t < lane; t++) dtt = dtt / 2;
-        const unsigned doneb = __ballot_sync(FULL, lane >= 1 && !(dtt > kp.time_tol));
-        kstar_all = __ffs(doneb) - 1;
-        dtk_all = __shfl_sync(FULL, dtt, kstar_all < 0 ? 0 : kstar_all);
-    }
+    halving_floor(kp, lane, kstar_all, dtk_all);
 
     const long long Wp = kp.Wp;
-    const unsigned long long count = min(*count_ptr, count_cap);  // (a capped list: classify_kernel's `cap`)
+    // (runner bits 1, 2: this launch only runs when the list is at least / less than BULK_LIST worlds long -- the host
+    //  launches both instances on the same list and the one that suits its length does the work)
+    if (((runner & 2) && *count_ptr < BULK_LIST) || ((runner & 4) && *count_ptr >= BULK_LIST)) return;
+    // spec rounds (SpecParams, fizz_common.cuh): the items of a launch are (list entry, slot) pairs
+    const bool SPEC = FAST && sp.enabled != 0;
+    const int SK = SPEC ? SPEC_K : 1;
+    const int SSW = spec_slot_words(F);
+    const unsigned long long count = min(*count_ptr, count_cap) * (unsigned long long)SK;  // (a capped list: classify_kernel's `cap`)
     const bool speculate = (kp.trace == nullptr);  // the contact trace needs every trial's tuples: sequential then
 
+    // Work distribution: the first item of every warp is static (CTA c takes items 4c .. 4c+3), the rest is pulled from
+    // the cursor.  A short list therefore keeps FEW CTAs resident (the others exit at once) instead of one warp in each:
+    // the launches that run beside this one (spec rounds, the other instance) find room.
+    bool first_item = true;
     for (;;) {
         unsigned long long idx = 0;
-        if (lane == 0) idx = atomicAdd(cursor, 1ULL);
-        idx = __shfl_sync(FULL, idx, 0);
+        if (first_item) {
+            idx = (unsigned long long)blockIdx.x * CONTACT_WARPS + warp;
+            first_item = false;
+        } else {
+            if (lane == 0) idx = (unsigned long long)gridDim.x * CONTACT_WARPS + atomicAdd(cursor, 1ULL);
+            idx = __shfl_sync(FULL, idx, 0);
+        }
         if (idx >= count) break;
-        const long long w = list[idx];
+        const unsigned long long wi = idx / (unsigned)SK;
+        const int slot = (int)(idx - wi * (unsigned)SK);
+        const long long w = list[wi];
         FIZZ_ASSERT(w >= 0 && w < kp.W);
 
         // ---- load the world into the warp's shared-memory slice ------------------------------------------------
-        if (lane < F) {
-            const double x = kp.pos[(2 * lane) * Wp + w], y = kp.pos[(2 * lane + 1) * Wp + w];
-            s.px[lane] = x; s.py[lane] = y; s.sx[lane] = x; s.sy[lane] = y;  // finish_update ended the last step
-            s.vx[lane] = kp.vel[(2 * lane) * Wp + w];
-            s.vy[lane] = kp.vel[(2 * lane + 1) * Wp + w];
-            s.thr[lane] = kp.thr[lane * Wp + w];
-            s.mass[lane] = kp.mass[lane * Wp + w];
+        double heat = kp.heat[w];
+        long long step = kp.steps[w];
+        long long target = kp.target_steps;          // where this item stops
+        // spec rounds: cost (fast-path calls + 10 x checks evaluated on the general path) at which the item stops at the next
+        // timestep boundary / is given up at once (only items that started from a PREDICTED state: a wrong prediction
+        // can be arbitrarily expensive to evaluate, and nobody needs its result)
+        const long long NOCAP = 0x3fffffffffffffffLL;
+        long long call_budget = NOCAP, abort_cap = NOCAP;
+        const long long t_item = clock64();   // cost is measured: 256 clock cycles a unit (one fast-path call, roughly)
+        long long t_step = t_item;
+        double *rec = nullptr;
+        [[maybe_unused]] const double heat0 = heat;
+        // spec round: this item is done (or has nothing to do); the warp that finishes the LAST item of a world commits
+        // the round for it (fizz_spec.cuh)
+        auto spec_item_done = [&]() {
+            __threadfence();
+            __syncwarp();
+            long long old = 0;
+            long long *cnt = sp.ctrl + w * SPEC_CTRL_WORDS + 4;
+            if (lane == 0) old = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cnt), 1ULL);
+            old = __shfl_sync(FULL, old, 0);
+            if (old == SPEC_K - 1) {
+                __threadfence();
+                if (lane == 0) *cnt = 0;
+                spec_commit(kp, sp, w, sp.slots + wi * (unsigned)SPEC_K * (size_t)SSW, lane);
+            }
+            __syncwarp();
+        };
+        {
+            double x = 0.0, y = 0.0, vx = 0.0, vy = 0.0;
+            if (lane < F) {
+                x = kp.pos[(2 * lane) * Wp + w]; y = kp.pos[(2 * lane + 1) * Wp + w];
+                vx = kp.vel[(2 * lane) * Wp + w]; vy = kp.vel[(2 * lane + 1) * Wp + w];
+            }
+            bool skip = step >= kp.target_steps;
+            // (a world that is at the target already -- listed by a reader that raced with another launch's write-back --
+            //  must not be touched: update() below runs before the target is tested)
+            if constexpr (FAST) {
+                if (SPEC) {
+                    // slot `slot` of this round: update() number step + slot * L ... of the world, from the PREDICTED state
+                    const long long *ctrl = sp.ctrl + w * SPEC_CTRL_WORDS;
+                    int Kw, Lw;
+                    spec_shape(kp.tier[w], sp.S, sp.D, Kw, Lw);
+                    const bool predictor = ctrl[0] > 1;
+                    // (ctrl[0] == -target: suspended for this chunk -- a timestep too long for a round, see below)
+                    skip = skip || step < 1 || kp.status[w] != 0 || slot >= (predictor ? Kw : 1) || ctrl[0] == -kp.target_steps;
+                    if (!skip && predictor) {
+                        const long long my_start = step + (long long)slot * Lw;
+                        if (my_start >= kp.target_steps) skip = true;
+                        if (my_start + Lw < target) target = my_start + Lw;
+                        if (!skip && lane < F && slot > 0) {
+                            const unsigned long long cw = (unsigned long long)ctrl[1 + (lane >> 2)];
+                            const int cx = (int)((cw >> (16 * (lane & 3))) & 255), cy = (int)((cw >> (16 * (lane & 3) + 8)) & 255);
+                            const double rdt = kp.time_disc - dtk_all;
+                            for (int t = slot * Lw; t > 0; t--) {
+                                spec_predict(x, vx, cx, kp.time_disc, rdt, kp.accx);
+                                spec_predict(y, vy, cy, kp.time_disc, rdt, kp.accy);
+                            }
+                        }
+                        step = my_start;
+                        if (slot > 0) abort_cap = 2LL * sp.D + 64;
+                    } else if (!skip) {
+                        // no usable predictor: this world advances sequentially, a bounded piece per round
+                        if (step + sp.budget_steps < target) target = step + sp.budget_steps;
+                        call_budget = sp.budget_cost;
+                    }
+                    // slot 0 does real work, but a round ends with its longest item: a timestep that takes several times the
+                    // round's length (a resolve loop of thousands of passes: the worlds the watchdog is about to stop) is
+                    // given up as well -- the world is suspended until the launch after the rounds has brought it to the chunk
+                    // target, one warp, beside everybody else's leftovers
+                    if (slot == 0) abort_cap = 4LL * sp.D;
+                    if (skip) { spec_item_done(); continue; }
+                    rec = sp.slots + (wi * (unsigned)SPEC_K + (unsigned)slot) * (size_t)SSW;
+                    if (lane < F) { rec[4 * lane] = x; rec[4 * lane + 1] = y; rec[4 * lane + 2] = vx; rec[4 * lane + 3] = vy; }
+                }
+            }
+            if (skip) continue;
+            if (lane < F) {
+                s.px[lane] = x; s.py[lane] = y; s.sx[lane] = x; s.sy[lane] = y;  // finish_update ended the last step
+                s.vx[lane] = vx; s.vy[lane] = vy;
+                s.thr[lane] = kp.thr[lane * Wp + w];
+                s.mass[lane] = kp.mass[lane * Wp + w];
+            }
         }
         for (int r = lane; r < 2 * V; r += 32) s.off[r] = kp.off[(size_t)r * Wp + w];
         for (int v = lane; v < V; v += 32) s.max_[v] = NAN;  // empty memo: NaN never compares equal
-        double heat = kp.heat[w];
-        long long step = kp.steps[w];
         const long long step_in = step;
-        // (a world that is at the target already -- listed by a reader that raced with another launch's write-back --
-        //  must not be touched: update() below runs before the target is tested)
-        if (step >= kp.target_steps) continue;
         long long status = 0;
         long long ncalls_total = 0, fast_calls = 0;
         __syncwarp();
@@ -652,6 +747,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
         int k = 0, ncalls = 0, ns = 0;
         int fast_step = 0, calm = 0;  // tier-3 bookkeeping (scheduling hint only)
         int last_calls = 0;           // check_collisions() of the last completed timestep (scheduling hint only)
+        int last_cost = 0;            // ... and what it cost, in units of 256 clock cycles (scheduling hint only)
         [[maybe_unused]] int two_fail = 0;  // consecutive failed attempts at the two-trapped-bodies shortcut
         bool trapped = false;
         int quiet = 0;        // consecutive contact-free timesteps: one check_collisions(), no tuple (scheduling hint)
@@ -704,6 +800,9 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             }
             ncalls++;
             ncalls_total++;
+            if constexpr (FAST) {
+                if (abort_cap != NOCAP && ((clock64() - t_item) >> 8) > abort_cap) { status = FIZZ_ST_SPEC_ABORT; break; }
+            }
 
             int nh = 0;
             double maxov = 0.0;  // :125-129
@@ -1037,7 +1136,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                                 if (which == 1 && rets[0] == TRAP_MIDSTEP) nc_in = kp.max_calls - cons[0];   // budget = pa checks
                                 int nc = nc_in;
                                 rets[which] = trapped_run<false, true>(s, kp, F, X, lane, which ? bB : bA, hx, nc, tot, st2, kk2, dt2, sh,
-                                                                       lc, kstar_all, dtk_all, &boxes[which]);
+                                                                       lc, kstar_all, dtk_all, target, NOCAP, NOCAP, &boxes[which]);
                                 cons[which] = nc - nc_in;
                                 valid = (hx == 0.0) && (which == 1 || rets[0] == TRAP_EMPTY || cons[0] >= 1);
                             }
@@ -1088,18 +1187,23 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     const int nb = kp.nv[b];
                     int ret = TRAP_MIDSTEP, steps_here = 0;
                     // (one instantiation for triangles and quadrilaterals; anything else stays on the general path)
+                    const long long t_call = clock64();
+                    const long long cost_now = (t_call - t_item) >> 8;
                     if (nb == 3 || nb == 4)
                         ret = trapped_run<FAST>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, step, k, dt, steps_here,
-                                                last_calls, kstar_all, dtk_all);
+                                                last_calls, kstar_all, dtk_all, target, call_budget - cost_now + ncalls_total,
+                                                abort_cap - cost_now + ncalls_total);
                     fast_calls += ncalls_total - before;
                     if (steps_here) {
                         // whole timesteps went by in registers: all of them trapped ones
                         trapped = true; calm = 0; quiet = 0; quiet_empty = 0; fast_step = 0;
+                        t_step = clock64();
+                        last_cost = (int)(((t_step - t_call) >> 8) / steps_here);
                     }
                     if (ret == TRAP_BOUNDARY) {
                         // a fresh update() (or the target): the vertices are derived state again
                         resolve = false; verts_explicit = false;
-                        if (step >= kp.target_steps) break;
+                        if (step >= target || (call_budget != NOCAP && ((clock64() - t_item) >> 8) >= call_budget)) break;
                         continue;
                     }
                     verts_explicit = true;
@@ -1128,6 +1232,11 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             __syncwarp();
             step++;                                            // :259
             last_calls = ncalls;
+            {
+                const long long now = clock64();
+                last_cost = (int)((now - t_step) >> 8);
+                t_step = now;
+            }
             quiet = (ncalls == 1) ? quiet + 1 : 0;  // (a step with a tuple makes at least two calls)
             quiet_empty = (ncalls == 1 && ns == 0) ? quiet_empty + 1 : 0;
             resolve = false; k = 0; dt = kp.time_disc; ncalls = 0;
@@ -1140,12 +1249,50 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 fast_step = 0;
                 if (heavy) trapped = true;  // flagged for the NEXT chunk; this chunk is finished here (no idle time)
             }
-            if (step >= kp.target_steps) break;
+            if (step >= target || (call_budget != NOCAP && ((clock64() - t_item) >> 8) >= call_budget)) break;
             verts_explicit = false;
         }
 
-        // ---- write the world back ----------------------------------------------------------------------------
         __syncwarp();
+        if constexpr (FAST) {
+            if (SPEC) {
+                // ---- spec round: the result goes to this item's slot record; the commit decides (fizz_spec.cuh) ------------
+                bool fin = true;
+                if (lane < F) {
+                    const double x = s.px[lane], y = s.py[lane];
+                    double *e = rec + 4 * F + 4 * lane;
+                    e[0] = x; e[1] = y; e[2] = s.vx[lane]; e[3] = s.vy[lane];
+                    fin = (fabs(x) < INFINITY) && (fabs(y) < INFINITY);
+                }
+                if (status == 0 && !__all_sync(FULL, fin)) status = FIZZ_ST_NONFINITE;
+                // slot 0 started from the real state: whatever it found is the world's (the vertices of a timestep that
+                // ended in a resolve pass are explicit state, written where a normal launch writes them)
+                if (slot == 0 && verts_explicit && status != FIZZ_ST_SPEC_ABORT)
+                    for (int r = lane; r < 2 * V; r += 32) kp.verts[(size_t)r * Wp + w] = s.vert[r];
+                if (lane == 0) {
+                    const bool clean = status == 0 && !verts_explicit &&
+                                       __double_as_longlong(heat) == __double_as_longlong(heat0);
+                    long long *m = reinterpret_cast<long long *>(rec + 8 * F);
+                    m[1] = step - step_in; m[2] = ncalls_total; m[3] = fast_calls; m[4] = last_calls;
+                    rec[8 * F + 5] = heat; m[6] = status; m[7] = verts_explicit ? 1 : 0;
+                    m[8] = ((clock64() - t_item) >> 8) / (step > step_in ? step - step_in : 1);   // cost per timestep of this item
+                    m[0] = 1 | (clean ? 2 : 0) | (status == FIZZ_ST_SPEC_ABORT ? 4 : 0);
+                    if (sp.dbg) {
+                        const unsigned long long cyc = (unsigned long long)(clock64() - t_item);
+                        atomicMax(sp.dbg + 4 * sp.round, cyc);
+                        atomicAdd(sp.dbg + 4 * sp.round + 1, cyc);
+                        atomicAdd(sp.dbg + 4 * sp.round + 2, 1ULL);
+                        if (status == FIZZ_ST_SPEC_ABORT) atomicAdd(sp.dbg + 4 * sp.round + 3, 1ULL);
+                    }
+                }
+                spec_item_done();
+                continue;
+            }
+        }
+#ifdef FIZZ_RUNNER_DEBUG
+        if (lane == 0 && w < 65536 && step_in >= 2688) atomicAdd(&g_dbg_cycles[w], (unsigned long long)(clock64() - t_item));
+#endif
+        // ---- write the world back ----------------------------------------------------------------------------
         bool finite = true;
         if (lane < F) {
             const double x = s.px[lane], y = s.py[lane];
@@ -1173,9 +1320,13 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             // a runner launch never releases its worlds itself (tier 4 = "owned by a runner"): it runs on its own stream,
             // and a work-list kernel of the chunk pipeline reading steps/tier while they are stored here could list a
             // finished world again.  The host demotes tier 4 after the join at the end of fizz_step().
-            if (runner) t = 4;
+            if (runner & 1) t = 4;
             // bits 8..31: check_collisions() of the last completed timestep: how heavy the world is NOW
-            kp.tier[w] = t | ((long long)(last_calls & 0xffffff) << 8);
+            // bits 32..55: cost per timestep, averaged over this launch's timesteps (fizz_common.cuh: spec_shape)
+            last_cost = (int)min((long long)0xffffff, ((clock64() - t_item) >> 8) / (step > step_in ? step - step_in : 1));
+            // bit 56: "the spec rounds cannot predict this world" (set by their commit step, sticky)
+            kp.tier[w] = t | ((long long)(last_calls & 0xffffff) << 8) | ((long long)(last_cost & 0xffffff) << 32) |
+                         (kp.tier[w] & (1LL << 56));
             atomicAdd(kp.counters + 1, (unsigned long long)(step - step_in));
             atomicAdd(kp.counters + 2, (unsigned long long)ncalls_total);
             atomicAdd(kp.counters + 3, (unsigned long long)fast_calls);
@@ -1186,14 +1337,15 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 
 // Work list for the contact kernel: every running world that has not reached the chunk target.
 // The tier word holds the scheduling hint in bits 0..7 and the check_collisions() count of the world's last completed
-// timestep in bits 8..31.  `use_rate`: only worlds whose last timestep made [rate_lo, rate_hi) calls
-// are taken: lets the host append the heaviest worlds first.
+// timestep in bits 8..31 and its cost in bits 32..55.  `use_rate`: only worlds whose last timestep made [rate_lo, rate_hi)
+// calls (1) or cost that much (2) are taken: lets the host append the heaviest worlds first / split the worlds between
+// the spec rounds and the ordinary launch.
 // `mark` >= 0: the selected worlds get tier = mark (runner mode: 4 = "owned by a runner launch", which keeps every other
 // kernel of the pipeline away from them until the host releases them after the join).
 __global__ void classify_kernel(const long long *status, const long long *steps, long long *tier, long long W,
                                 long long target, long long tier_lo, long long tier_hi, int use_rate,
                                 long long rate_lo, long long rate_hi, long long *list, unsigned long long *count,
-                                long long mark = -1, unsigned long long cap = ~0ull) {
+                                long long mark = -1, unsigned long long cap = ~0ull, int flagmode = 0) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long tw = 0;
     bool lag = false;
@@ -1203,8 +1355,11 @@ __global__ void classify_kernel(const long long *status, const long long *steps,
         lag = status[w] == 0 && t >= tier_lo && t <= tier_hi && steps[w] < target;
     }
     if (lag && use_rate) {
-        const long long r = (tw >> 8) & 0xffffff;
-        lag = r >= rate_lo && r < rate_hi;
+        const long long r = (use_rate == 2) ? ((tw >> 32) & 0xffffff) : ((tw >> 8) & 0xffffff);   // 2: by cost
+        const bool in = r >= rate_lo && r < rate_hi, nospec = ((tw >> 56) & 1) != 0;
+        // flagmode 1: the spec list (in range and predictable); 2: its complement (below the range, or unpredictable);
+        // ... 3: in range and unpredictable (the runner launches of spec mode)
+        lag = (flagmode == 1) ? (in && !nospec) : ((flagmode == 2) ? (in || nospec) : ((flagmode == 3) ? (in && nospec) : in));
     }
     const unsigned b = __ballot_sync(0xffffffffu, lag);
     if (b == 0) return;

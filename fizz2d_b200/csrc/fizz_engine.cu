@@ -195,6 +195,17 @@ struct FizzGroup {
     long long rcap;              // entries per list: one warp per world, one CTA per SM, a third of the SMs at most
                                  // (runner CTAs keep their SMs to themselves: the chunk pipeline needs the rest)
     unsigned long long *rcount;  // [NR][2] count, cursor
+    // spec rounds (fizz_common.cuh: SpecParams): time-parallel stepping of the heavy trapped worlds, chunk by chunk
+    bool spec_on;
+    int spec_S, spec_D, spec_cost, spec_budget, spec_slack;
+    long long scap;              // entries of the spec list
+    long long *spec_list;        // [scap]                       (all of it allocated on first use)
+    double *spec_slots;          // [scap][SPEC_K][slot words]
+    long long *spec_ctrl;        // [W][SPEC_CTRL_WORDS]
+    unsigned long long *spec_count;   // [0] list length, [1 + r] work cursor of round r of the current fizz_step() call
+    cudaStream_t spec_stream;
+    cudaEvent_t spec_fork, spec_join;
+    static const int SPEC_RMAX = 4096;
     unsigned long long *sched_count;  // [0] = count, [1] = cursor
     unsigned char *vbody_dev;
     // optional per-kernel timing (fizz_set_profiling)
@@ -317,6 +328,24 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     g->profile = false; g->ev_used = 0; g->prof_error = cudaSuccess;
     g->side = nullptr; g->ev_fork = nullptr; g->ev_join = nullptr;
     g->rlist = nullptr; g->rcount = nullptr;
+    g->spec_list = nullptr; g->spec_slots = nullptr; g->spec_ctrl = nullptr; g->spec_count = nullptr;
+    g->spec_stream = nullptr; g->spec_fork = nullptr; g->spec_join = nullptr;
+    {
+        auto env_int = [](const char *name, long long dflt, long long lo, long long hi) {
+            const char *v = std::getenv(name);
+            if (!v || !*v) return dflt;
+            const long long x = std::atoll(v);
+            return x < lo ? lo : (x > hi ? hi : x);
+        };
+        g->spec_on = env_int("FIZZ_SPEC", 1, 0, 1) != 0;
+        g->spec_S = (int)env_int("FIZZ_SPEC_S", 32, 2, 512);          // timesteps per world and round
+        g->spec_D = (int)env_int("FIZZ_SPEC_D", 700, 1, 1 << 20);     // cost per item (~0.13 us per unit)
+        g->spec_cost = (int)env_int("FIZZ_SPEC_COST", 48, 1, 1 << 20);  // worlds at least this costly per timestep
+        g->spec_budget = (int)env_int("FIZZ_SPEC_BUDGET", 0, 0, 1 << 30);   // 0: D
+        g->spec_slack = (int)env_int("FIZZ_SPEC_SLACK", 8, 4, 64);    // rounds = slack/4 x the rounds of a perfect predictor
+        g->scap = env_int("FIZZ_SPEC_CAP", 4096, 1, 1 << 20);
+        if (g->scap > n_worlds) g->scap = n_worlds;
+    }
     for (int i = 0; i < FizzGroup::NR; i++) { g->rstream[i] = nullptr; g->rdone[i] = nullptr; }
     for (int i = 0; i < 3; i++) { g->prof_ms[i] = 0.0; g->prof_launches[i] = 0; }
     KParams &kp = g->kp;
@@ -457,6 +486,13 @@ int fizz_group_destroy(FizzGroup *g) {
             if (g->rstream[i]) cudaStreamDestroy(g->rstream[i]);
         }
         if (g->rlist) cudaFree(g->rlist);
+        if (g->spec_list) cudaFree(g->spec_list);
+        if (g->spec_slots) cudaFree(g->spec_slots);
+        if (g->spec_ctrl) cudaFree(g->spec_ctrl);
+        if (g->spec_count) cudaFree(g->spec_count);
+        if (g->spec_fork) cudaEventDestroy(g->spec_fork);
+        if (g->spec_join) cudaEventDestroy(g->spec_join);
+        if (g->spec_stream) cudaStreamDestroy(g->spec_stream);
         if (g->rcount) cudaFree(g->rcount);
     }
     delete g;
@@ -595,12 +631,45 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     // before the join below, and a runner waits for nothing.  Short calls (per-timestep stepping) do not bother.
     const long long final_target = g->target + n_steps;
 #ifdef FIZZ_RUNNER_DEBUG
-    cudaEvent_t d0 = nullptr, d_chunk[64] = {};
+    cudaEvent_t d0 = nullptr, d_chunk[64] = {}, d_spec[64] = {}, d_ball[64] = {}, d_main[64] = {};
+    static unsigned long long d_cnt[64][9];
+    std::memset(d_cnt, 0, sizeof(d_cnt));
+    static unsigned long long *d_sdbg = nullptr;
+    long long d_round0[66] = {};
+    if (!d_sdbg) cudaMalloc(&d_sdbg, sizeof(unsigned long long) * 4 * FizzGroup::SPEC_RMAX);
+    cudaMemsetAsync(d_sdbg, 0, sizeof(unsigned long long) * 4 * FizzGroup::SPEC_RMAX, st);
     long long d_len[64] = {};
     cudaEventCreate(&d0);
     cudaEventRecord(d0, st);
 #endif
+    // spec rounds (FIZZ_MODE_HYBRID, calls of >= 128 timesteps): in every chunk after the first, the trapped worlds whose
+    // timesteps are expensive are brought to the chunk target time-parallel (fizz_common.cuh: SpecParams) on a library-owned
+    // stream, beside the launch that steps everything else; whatever the rounds leave is finished by a launch after the
+    // join.  Not with the contact trace on (its records would come from discarded slots too).  With spec rounds there are
+    // no runner launches: no world's chain is long enough to be worth skipping the chunk boundaries for.
+    const bool spec = (g->mode == FIZZ_MODE_HYBRID) && n_steps >= 128 && g->spec_on && kp.trace == nullptr;
     const bool runners = (g->mode == FIZZ_MODE_HYBRID) && n_steps >= 128;
+    const SpecParams no_spec = {};
+    SpecParams sp = {};
+    long long spec_round = 0;
+    if (spec) {
+        if (!g->spec_slots) {
+            const size_t slot_words = (size_t)g->scap * SPEC_K * (size_t)spec_slot_words(F);
+            const size_t ctrl_words = (size_t)g->lay.n_worlds * SPEC_CTRL_WORDS;
+            CU(cudaMalloc(&g->spec_list, sizeof(long long) * (size_t)g->scap));
+            CU(cudaMalloc(&g->spec_slots, sizeof(double) * slot_words));
+            CU(cudaMalloc(&g->spec_ctrl, sizeof(long long) * ctrl_words));
+            CU(cudaMalloc(&g->spec_count, sizeof(unsigned long long) * (1 + FizzGroup::SPEC_RMAX)));
+            CU(cudaMemset(g->spec_slots, 0, sizeof(double) * slot_words));
+            CU(cudaMemset(g->spec_ctrl, 0, sizeof(long long) * ctrl_words));
+            CU(cudaStreamCreateWithFlags(&g->spec_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&g->spec_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g->spec_join, cudaEventDisableTiming));
+        }
+        sp.slots = g->spec_slots; sp.ctrl = g->spec_ctrl;
+        sp.S = g->spec_S; sp.D = g->spec_D; sp.budget_cost = g->spec_budget > 0 ? g->spec_budget : g->spec_D; sp.budget_steps = 32; sp.enabled = 1;
+        CU(cudaMemsetAsync(g->spec_count, 0, sizeof(unsigned long long) * (1 + FizzGroup::SPEC_RMAX), st));
+    }
     bool rused[FizzGroup::NR] = {};
     int rnext = 0;
     const unsigned long long runner_cap = (unsigned long long)g->rcap;  // all resident at once, see FizzGroup::rcap
@@ -629,6 +698,9 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             g->launches += 2;
         }
         cudaEvent_t eb = g->profile ? next_event(g, st) : nullptr;
+#ifdef FIZZ_RUNNER_DEBUG
+        if (nchunk < 64) { cudaEventCreate(&d_ball[nchunk]); cudaEventRecord(d_ball[nchunk], st); }
+#endif
         CU(cudaMemsetAsync(g->sched_count, 0, 4 * sizeof(unsigned long long), st));
         if (g->mode == FIZZ_MODE_HYBRID || g->mode == FIZZ_MODE_HYBRID_SYNC) {
             // (nothing is flagged before the first chunk has run; a stream is used once per call: a second launch on it
@@ -648,15 +720,23 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                 // sharing SMs with the chunk pipeline makes the longest chain 0-20 % slower depending on where it lands
                 // (540-640 ms per pass), alone it is 545-560 ms every time (no runners: 580-620)
                 // (two passes so that the very heaviest get their slots first when the cap bites)
+                if (spec) {
+                    // spec mode: the runner launches take the expensive worlds the spec rounds cannot predict (bit 56 of the
+                    // tier word: e.g. two free bodies stuck together far from the scene) -- inherently sequential chains,
+                    // which should neither stop at chunk boundaries nor share an SM with anything
+                    classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 0, 3, 2,
+                                                           g->spec_cost, 1LL << 40, rl, rc, 4, runner_cap, 3);
+                } else {
                 classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, 1,
                                                        3 * runner_rate, 1LL << 40, rl, rc, 4, runner_cap);
                 classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, final_target, 3, 3, 1,
                                                        runner_rate, 3 * runner_rate, rl, rc, 4, runner_cap);
+                }
                 CU(cudaEventRecord(g->ev_fork, st));
                 CU(cudaStreamWaitEvent(g->rstream[slot], g->ev_fork, 0));
                 KParams kr = kp;
                 kr.target_steps = final_target;
-                contact_kernel<true><<<rgrid, CONTACT_BLOCK, runner_smem, g->rstream[slot]>>>(kr, rl, rc, rc + 1, runner_cap, 1);
+                contact_kernel<true><<<rgrid, CONTACT_BLOCK, runner_smem, g->rstream[slot]>>>(kr, rl, rc, rc + 1, runner_cap, 1, no_spec);
                 rused[slot] = true;
                 g->launches += 2;
             }
@@ -664,16 +744,75 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             // world with the longest chain of resolve passes never waits for anything
             // (work list in world order: measured -- grouping the trapped worlds at the head of the list, or sorting them
             //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
-            classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
-                                                   g->sched_list, g->sched_count);   // (tier 4: owned by a runner)
+            bool spec_chunk = false;
+            if (spec && g->target > c) {
+                // rounds for this chunk: enough for a world that is predicted right half of the time
+                long long rounds = ((long long)c * g->spec_slack / 4 + g->spec_S - 1) / g->spec_S + 2;
+                if (spec_round + rounds > FizzGroup::SPEC_RMAX) rounds = FizzGroup::SPEC_RMAX - spec_round;
+                if (rounds > 0) {
+                    spec_chunk = true;
+                    // the trapped worlds whose last timestep cost >= spec_cost (list in world order, rebuilt every chunk: a
+                    // world leaves when its contact ends); a listed world is left alone by the launch beside the rounds
+                    CU(cudaMemsetAsync(g->spec_count, 0, sizeof(unsigned long long), st));
+                    classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 2, g->spec_cost,
+                                                           1LL << 40, g->spec_list, g->spec_count, -1,
+                                                           (unsigned long long)g->scap, 1);
+                    // everything else that lags (same selection, complemented) -- listed BEFORE the rounds start: their
+                    // commit steps rewrite the tier words this selection reads
+                    classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 2, 0, g->spec_cost,
+                                                           g->sched_list, g->sched_count, -1, ~0ull, 2);
+                    CU(cudaEventRecord(g->spec_fork, st));
+                    CU(cudaStreamWaitEvent(g->spec_stream, g->spec_fork, 0));
+                    const long long sneed = g->scap * SPEC_K / CONTACT_WARPS;
+                    const dim3 sgrid((unsigned)(sneed < tfull ? sneed : tfull));
+                    for (long long r = 0; r < rounds; r++, spec_round++) {
+#ifdef FIZZ_RUNNER_DEBUG
+                        sp.round = (int)spec_round; sp.dbg = d_sdbg;
+                        if (nchunk < 64) d_round0[nchunk + 1] = spec_round + 1;
+#endif
+                        contact_kernel<true><<<sgrid, CONTACT_BLOCK, g->contact_smem, g->spec_stream>>>(
+                            kp, g->spec_list, g->spec_count, g->spec_count + 1 + spec_round, (unsigned long long)g->scap, 0, sp);
+                    }
+                    CU(cudaEventRecord(g->spec_join, g->spec_stream));
+#ifdef FIZZ_RUNNER_DEBUG
+                    if (nchunk < 64) { cudaEventCreate(&d_spec[nchunk]); cudaEventRecord(d_spec[nchunk], g->spec_stream); }
+#endif
+                    g->launches += rounds + 1;
+                }
+            }
+            if (!spec_chunk) {
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
+                                                       g->sched_list, g->sched_count);   // (tier 4: owned by a runner)
+            }
             // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
             // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
-            if (g->target == c)
+            if (g->target == c) {
                 contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                     g->sched_count + 1);
-            else
+                                                                                     g->sched_count + 1, ~0ull, 0, no_spec);
+            } else if (spec) {
+                // with the expensive worlds in the spec rounds, a long list is a throughput phase again (the scene stays
+                // busy for a few hundred timesteps): both instances are launched, the one the list length suits runs
+                contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                     g->sched_count + 1, ~0ull, 2, no_spec);
                 contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                    g->sched_count + 1);
+                                                                                    g->sched_count + 1, ~0ull, 4, no_spec);
+                g->launches++;
+            } else {
+                contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                    g->sched_count + 1, ~0ull, 0, no_spec);
+            }
+#ifdef FIZZ_RUNNER_DEBUG
+            if (nchunk < 64) { cudaEventCreate(&d_main[nchunk]); cudaEventRecord(d_main[nchunk], st); }
+#endif
+            if (spec_chunk) {
+                // join, then whatever the rounds left short of the chunk target (and worlds beyond the list's capacity)
+                CU(cudaStreamWaitEvent(st, g->spec_join, 0));
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
+                                                       g->sched_list2, g->sched_count + 2);
+                contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list2, g->sched_count + 2,
+                                                                                    g->sched_count + 3, ~0ull, 0, no_spec);
+                g->launches += 4;
+            }
             g->launches -= 2;
         } else {
             // throughput-tuned (hybrid3): two instances run SIDE BY SIDE on disjoint worlds -- the trapped instance (tier
@@ -687,10 +826,10 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             CU(cudaEventRecord(g->ev_fork, st));
             CU(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
             contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, g->side>>>(kp, g->sched_list2, g->sched_count + 2,
-                                                                                     g->sched_count + 3);
+                                                                                     g->sched_count + 3, ~0ull, 0, no_spec);
             CU(cudaEventRecord(g->ev_join, g->side));
             contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                 g->sched_count + 1);
+                                                                                 g->sched_count + 1, ~0ull, 0, no_spec);
             CU(cudaStreamWaitEvent(st, g->ev_join, 0));
         }
         if (g->profile) {
@@ -703,14 +842,19 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         g->launches += 6;
         done += c;
 #ifdef FIZZ_RUNNER_DEBUG
-        if (nchunk < 64) { cudaEventCreate(&d_chunk[nchunk]); cudaEventRecord(d_chunk[nchunk], st); d_len[nchunk] = c; }
+        if (nchunk < 64) {
+            cudaEventCreate(&d_chunk[nchunk]); cudaEventRecord(d_chunk[nchunk], st); d_len[nchunk] = c;
+            cudaMemcpyAsync(d_cnt[nchunk], kp.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(&d_cnt[nchunk][4], g->sched_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            if (spec) cudaMemcpyAsync(&d_cnt[nchunk][8], g->spec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        }
 #endif
     }
     bool any = false;
 #ifdef FIZZ_RUNNER_DEBUG
-    cudaEvent_t d_main = nullptr, d_run[FizzGroup::NR] = {};
-    cudaEventCreate(&d_main);
-    cudaEventRecord(d_main, st);
+    cudaEvent_t d_mainend = nullptr, d_run[FizzGroup::NR] = {};
+    cudaEventCreate(&d_mainend);
+    cudaEventRecord(d_mainend, st);
     for (int i = 0; i < FizzGroup::NR; i++)
         if (rused[i]) { cudaEventCreate(&d_run[i]); cudaEventRecord(d_run[i], g->rstream[i]); }
 #endif
@@ -729,7 +873,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                                                g->sched_list, g->sched_count);
         kp.target_steps = final_target;
         contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                            g->sched_count + 1);
+                                                                            g->sched_count + 1, ~0ull, 0, no_spec);
         CU(cudaGetLastError());
         g->launches += 2;
     }
@@ -737,7 +881,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     {
         cudaStreamSynchronize(st);
         float t = 0;
-        cudaEventElapsedTime(&t, d0, d_main);
+        cudaEventElapsedTime(&t, d0, d_mainend);
         fprintf(stderr, "[runner debug] main pipeline done at %.1f ms;", t);
         for (int i = 0; i < FizzGroup::NR; i++)
             if (d_run[i]) { cudaEventElapsedTime(&t, d0, d_run[i]); fprintf(stderr, " runner%d %.1f", i, t); cudaEventDestroy(d_run[i]); }
@@ -745,11 +889,85 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         cudaMemcpy(rc, g->rcount, sizeof(rc), cudaMemcpyDeviceToHost);
         fprintf(stderr, " | chunks (len@ms):");
         for (int i = 0; i < 64; i++)
-            if (d_chunk[i]) { cudaEventElapsedTime(&t, d0, d_chunk[i]); fprintf(stderr, " %lld@%.1f", d_len[i], t); cudaEventDestroy(d_chunk[i]); }
+            if (d_chunk[i]) { cudaEventElapsedTime(&t, d0, d_chunk[i]); fprintf(stderr, " %lld@%.1f", d_len[i], t); }
+        fprintf(stderr, "\n  per chunk: [ballistic done, main list done, chunk done] ms | cumulative: ballistic world-steps, contact world-steps, calls, fast calls | main list, straggler list, spec list");
+        for (int i = 0; i < 64; i++)
+            if (d_chunk[i]) {
+                float tb = 0, tm = 0;
+                cudaEventElapsedTime(&t, d0, d_chunk[i]);
+                if (d_ball[i]) { cudaEventElapsedTime(&tb, d0, d_ball[i]); cudaEventDestroy(d_ball[i]); }
+                if (d_main[i]) { cudaEventElapsedTime(&tm, d0, d_main[i]); cudaEventDestroy(d_main[i]); }
+                fprintf(stderr, "\n   chunk %2d: [%.1f %.1f %.1f] | %llu %llu %llu %llu | %llu %llu %llu", i, tb, tm, t, d_cnt[i][0], d_cnt[i][1],
+                        d_cnt[i][2], d_cnt[i][3], d_cnt[i][4], d_cnt[i][6], d_cnt[i][8]);
+                cudaEventDestroy(d_chunk[i]);
+            }
         fprintf(stderr, " | list sizes:");
         for (int i = 0; i < FizzGroup::NR; i++) fprintf(stderr, " %llu", rc[2 * i]);
+        if (spec) {
+            fprintf(stderr, "\n  spec rounds end at (ms):");
+            for (int i = 0; i < 64; i++)
+                if (d_spec[i]) { cudaEventElapsedTime(&t, d0, d_spec[i]); fprintf(stderr, " %.1f", t); cudaEventDestroy(d_spec[i]); }
+            std::vector<long long> c((size_t)W * SPEC_CTRL_WORDS);
+            cudaMemcpy(c.data(), g->spec_ctrl, sizeof(long long) * c.size(), cudaMemcpyDeviceToHost);
+            long long n = 0, acc = 0, ev = 0, miss = 0, blind = 0, rounds = 0;
+            for (long long w = 0; w < W; w++) {
+                const long long *x = c.data() + w * SPEC_CTRL_WORDS;
+                if (x[9] == 0) continue;
+                n++; acc += x[5]; ev += x[6]; miss += x[7]; blind += x[8]; rounds += x[9];
+            }
+            {
+                std::vector<unsigned long long> sd(4 * FizzGroup::SPEC_RMAX);
+                cudaMemcpy(sd.data(), d_sdbg, sizeof(unsigned long long) * sd.size(), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "\n  spec rounds per chunk: rounds with work / launched | longest item mean, max (us at 1.965 GHz) | item time total (ms) | items, given up");
+                long long prev = 0;
+                for (int i = 1; i < 65; i++) {
+                    if (!d_round0[i]) continue;
+                    long long used = 0, items = 0, ab = 0;
+                    double sum_max = 0, mx = 0, tot = 0;
+                    for (long long r = prev; r < d_round0[i]; r++) {
+                        if (sd[4 * r + 2] == 0) continue;
+                        used++; sum_max += sd[4 * r] / 1965.0; mx = std::max(mx, sd[4 * r] / 1965.0); tot += sd[4 * r + 1] / 1965.0e3;
+                        items += sd[4 * r + 2]; ab += sd[4 * r + 3];
+                    }
+                    fprintf(stderr, "\n   chunk %2d: %lld / %lld | %.0f %.0f | %.1f | %lld %lld", i - 1, used, d_round0[i] - prev, used ? sum_max / used : 0.0, mx,
+                            tot, items, ab);
+                    prev = d_round0[i];
+                }
+            }
+            {
+                std::vector<long long> tw((size_t)W);
+                cudaMemcpy(tw.data(), kp.tier, sizeof(long long) * (size_t)W, cudaMemcpyDeviceToHost);
+                std::vector<long long> idx;
+                for (long long w = 0; w < W; w++) if (c[w * SPEC_CTRL_WORDS + 9]) idx.push_back(w);
+                std::sort(idx.begin(), idx.end(), [&](long long a, long long b) {
+                    return c[a * SPEC_CTRL_WORDS + 9] - c[a * SPEC_CTRL_WORDS + 5] / 32 > c[b * SPEC_CTRL_WORDS + 9] - c[b * SPEC_CTRL_WORDS + 5] / 32; });
+                fprintf(stderr, "\n  worst worlds (rounds - accepted/32): world rounds accepted evaluated mispredicted blind | calls cost tier | classes");
+                for (size_t i = 0; i < idx.size() && i < 16; i++) {
+                    const long long *x = c.data() + idx[i] * SPEC_CTRL_WORDS;
+                    fprintf(stderr, "\n   %lld: %lld %lld %lld %lld %lld | %lld %lld %lld | %016llx %016llx", idx[i], x[9], x[5], x[6], x[7], x[8],
+                            (tw[idx[i]] >> 8) & 0xffffff, (tw[idx[i]] >> 32) & 0xffffff, tw[idx[i]] & 255, (unsigned long long)x[1], (unsigned long long)x[2]);
+                }
+            }
+            {
+                std::vector<unsigned long long> cyc(65536);
+                cudaMemcpyFromSymbol(cyc.data(), g_dbg_cycles, sizeof(unsigned long long) * 65536);
+                std::vector<long long> tw((size_t)W);
+                cudaMemcpy(tw.data(), kp.tier, sizeof(long long) * (size_t)W, cudaMemcpyDeviceToHost);
+                std::vector<int> idx(std::min<long long>(W, 65536));
+                for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+                std::sort(idx.begin(), idx.end(), [&](int a, int b) { return cyc[a] > cyc[b]; });
+                fprintf(stderr, "\n  ordinary-launch time from timestep 2688 on (cumulative over calls): world ms | calls cost tier flag | spec rounds accepted");
+                for (int i = 0; i < 12 && i < (int)idx.size(); i++) {
+                    const int w = idx[i];
+                    fprintf(stderr, "\n   %d: %.1f | %lld %lld %lld %lld | %lld %lld", w, cyc[w] / 1.965e6, (tw[w] >> 8) & 0xffffff, (tw[w] >> 32) & 0xffffff,
+                            tw[w] & 255, (tw[w] >> 56) & 1, c[(size_t)w * SPEC_CTRL_WORDS + 9], c[(size_t)w * SPEC_CTRL_WORDS + 5]);
+                }
+            }
+            fprintf(stderr, "\n  spec (cumulative): %lld worlds, %lld launches this call; timesteps accepted %lld of %lld evaluated; world-rounds %lld, "
+                    "%lld mispredicted, %lld without a predictor", n, spec_round, acc, ev, rounds, miss, blind);
+        }
         fprintf(stderr, "\n");
-        cudaEventDestroy(d_main); cudaEventDestroy(d0);
+        cudaEventDestroy(d_mainend); cudaEventDestroy(d0);
     }
 #endif
     return FIZZ_OK;
