@@ -423,6 +423,7 @@ class Bench:
             sampler.start()
         launches0 = sum(i["launches"] for i in bw.kernel_info())
         bw.counters(reset=True)
+        bw.spec_stats(reset=True)
         bw.profile(reset=True)
         bw.set_profiling(True)
         ev = []
@@ -440,6 +441,7 @@ class Bench:
         launches = sum(i["launches"] for i in bw.kernel_info()) - launches0
         profs = bw.profile(reset=True)
         cnts = bw.counters(reset=True)
+        spec_stats = bw.spec_stats(reset=True)
         bw.set_profiling(False)
         t_ms = sum(a.elapsed_time(b) for a, b in ev)
         steps_done, status, calls = bw.steps_done(), bw.status(), bw.calls()
@@ -460,7 +462,7 @@ class Bench:
         e2e_steps = int(sum(r["steps"].sum() for r in res))
         self.barrier()
         return dict(t_ms=t_ms, e2e_ms=sum(e2e_ms), world_steps=int(steps_done.sum()), e2e_world_steps=e2e_steps,
-                    launches=int(launches), profs=profs, cnts=cnts, status=status, calls=calls,
+                    launches=int(launches), profs=profs, cnts=cnts, spec_stats=spec_stats, status=status, calls=calls,
                     clocks=sampler.summary() if sampler else None)
 
 
@@ -496,8 +498,9 @@ def kernel_tables(b, m, steps, ops_per_ws, peak_tflops):
         # the library's spans are taken on the caller's stream; the runner launches of the contact kernel (trapped worlds,
         # library-owned streams) overlap them and end with the pass.  Contact kernels are busy whenever the ballistic
         # kernel is not: that is the time the roofline of the contact kernel is taken over.
-        note = ("contact ms = pass - ballistic (runner launches of the contact kernel overlap the chunk pipeline; the "
-                "caller-stream spans alone were %.1f ms per pass)" % (prof["contact"][0] / steps))
+        note = ("contact ms = pass - ballistic (the spec rounds and the runner launches of the contact kernel run on library-"
+                "owned streams beside the chunk pipeline; the caller-stream spans alone were %.1f ms per pass)"
+                % (prof["contact"][0] / steps))
         prof["contact"][0] = max(m["t_ms"] - prof["ballistic"][0], prof["contact"][0])
     info = infos[0]
     kernels = {k: {"ms_per_pass": prof[k][0] / steps, "launches_per_pass": prof[k][1] // steps,
@@ -511,10 +514,19 @@ def kernel_tables(b, m, steps, ops_per_ws, peak_tflops):
     if "contact" in kernels and b.mode == "hybrid":
         t = info["trapped"]
         kernels["contact"]["instances"] = {
-            "contact_kernel<false> (first chunk)": {"regs": info["contact"]["regs"], "blocks_per_sm": info["contact"]["blocks_per_sm"]},
-            "contact_kernel<true> (all later chunks, runner launches)": {"regs": t["regs"], "blocks_per_sm": t["blocks_per_sm"]}}
+            "contact_kernel<false> (throughput phase: chunks whose work list is >= 16384 worlds long)":
+                {"regs": info["contact"]["regs"], "blocks_per_sm": info["contact"]["blocks_per_sm"]},
+            "contact_kernel<true> (all later chunks, the spec rounds, runner launches)":
+                {"regs": t["regs"], "blocks_per_sm": t["blocks_per_sm"]}}
     dom = max(prof, key=lambda k: prof[k][0]) if prof else None
     out = {"kernels": kernels, "dominant_kernel": dom, "work": {k: v // steps for k, v in cnt.items()}}
+    sr = {}
+    for c in m.get("spec_stats", []):
+        for k, v in c.items():
+            sr[k] = sr.get(k, 0) + int(v)
+    if sr.get("rounds"):
+        # time-parallel stepping of the expensive worlds: per pass
+        out["work"]["spec_rounds"] = {k: v // steps for k, v in sr.items()}
     if ops_per_ws is None or not prof:
         return out
     # quiescent closed form per group: 12F + 2V + 8P ops per world-step, weighted by the ballistic steps
@@ -600,8 +612,8 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": t_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak",
                 "scaling_note": "weak scaling: every GPU steps its own %d worlds of an N x %d population.  Read as STRONG "
-                                "scaling (the same %d worlds over N GPUs) config 3 is flat: one world's sequential chain "
-                                "of resolve passes bounds the pass on any number of GPUs (DESIGN.md section 6)"
+                                "scaling (the same %d worlds over N GPUs) config 3 gains little: the chains of its trapped "
+                                "worlds, time-parallel as they are stepped, bound the pass (DESIGN.md sections 5d, 6)"
                                 % (args.worlds, args.worlds, args.worlds),
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world_size),
@@ -646,8 +658,9 @@ def run_gpu(args):
         line.update(kernel_tables(b, m, args.steps, ops_per_ws, peak_tflops))
         if "roofline" in line:
             s0 = specs[0]
-            line["roofline"]["note"] = ("the dominant kernel is latency-bound: a pass ends when the world with the longest "
-                                        "sequential chain of resolve passes ends (DESIGN.md, 'critical path')")
+            line["roofline"]["note"] = ("the dominant kernel is latency-bound: every chunk of a pass ends when its slowest "
+                                        "chain of resolve passes ends -- trapped worlds, stepped time-parallel by the spec "
+                                        "rounds, and the worlds no predictor fits (DESIGN.md, 'critical path')")
             line["roofline"]["hbm"] = hbm_view(sum(8 * s.n_worlds * 2 * (4 * s.n_free + 1) for s in specs),
                                                sum(v["launches_per_pass"] for v in line["kernels"].values()) * args.steps,
                                                m["t_ms"])

@@ -513,6 +513,22 @@ class BatchedWorld:
                             fast_path_calls=a[3]))
         return out
 
+    def set_spec(self, enabled=-1, window0=0, slot_cost=0, min_cost=0):
+        """Spec rounds (time-parallel stepping of expensive worlds in mode "hybrid"; include/fizz_b200.h: fizz_set_spec).
+        Results never depend on these settings."""
+        for g in self.groups:
+            _lib.check(_lib.load().fizz_set_spec(g.handle, int(enabled), int(window0), int(slot_cost), int(min_cost)))
+        return self
+
+    def spec_stats(self, reset=True):
+        """Per group: what the spec rounds did since the last reset."""
+        out = []
+        for k, g in enumerate(self.groups):
+            a = (C.c_int64 * 4)()
+            _lib.check(_lib.load().fizz_spec_stats(g.handle, a, 1 if reset else 0, C.c_void_p(self._stream_ptr(k))))
+            out.append(dict(timesteps_accepted=a[0], timesteps_evaluated=a[1], rounds=a[2], rounds_with_rejection=a[3]))
+        return out
+
     def kernel_info(self):
         info = []
         for g in self.groups:

@@ -27,7 +27,8 @@ struct KParams {
     double *verts;
     const double *fixed_geom;  // [FV][6]: x, y, unit normal of edge k->k+1 (nx, ny), own projection (lo, hi)
     unsigned long long *counters;  // [0] world-steps advanced by the ballistic kernel, [1] by the contact kernel,
-                                   // [2] check_collisions() made by the contact kernel, [3] of those in the fast path
+                                   // [2] check_collisions() made by the contact kernel, [3] of those in the fast path,
+                                   // [4..7] spec rounds: timesteps accepted, evaluated, rounds, rounds with a rejection
     long long *general_calls;      // optional, per world: check_collisions() made OUTSIDE the single-contact fast path
     FizzContact *trace;
     unsigned long long *trace_count;
@@ -47,50 +48,70 @@ struct KParams {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Time-parallel stepping of heavy worlds ("spec rounds"; fizz_spec.cuh, fizz_engine.cu: fizz_step).
+// Time-parallel stepping of expensive worlds ("spec rounds"; fizz_spec.cuh, fizz_engine.cu: fizz_step).
 // A world is a sequential chain (update() t+1 needs the state update() t left), but the state a trapped world starts its
 // next timestep from is almost always PREDICTABLE without running the timestep: the trapped coordinate comes back to
 // the same value, everything else moved ballistically.  So K warps evaluate update() t, t+L, t+2L, ... of one world
-// side by side, warp k starting from the state predicted for timestep t + kL, and a commit step accepts the longest
-// prefix of slots whose START state equals, bit for bit, the END state of the slot before (slot 0 starts from the real
-// state).  An accepted slot ran the real update() on the real state, so its result is the reference's; a mispredicted
-// slot is thrown away and its timesteps are evaluated again in the next round.  Results never depend on the predictor.
+// side by side (a ROUND), warp k starting from the state predicted for timestep t + kL, and a commit step accepts the
+// longest prefix of slots whose START state equals, bit for bit, the END state of the slot before (slot 0 starts from the
+// real state).  An accepted slot ran the real update() on the real state, so its result is the reference's; a
+// mispredicted slot is thrown away and its timesteps are evaluated again in the next round.  Results never depend on the
+// predictor, the window, or any other hint below.
 //
 // Slot record (doubles / 64-bit words), one per (list entry, slot), SPEC_K slots per list entry:
 //   [0, 4F)   start state: x, y, vx, vy of every free body      [4F, 8F) end state
 //   [8F + 0]  flags: bit 0 "ran", bit 1 "clean" (status 0, heat bit-identical to the world's, vertices derived)
 //   [8F + 1]  timesteps advanced   [8F + 2] check_collisions() made   [8F + 3] ... of those in the fast path
 //   [8F + 4]  check_collisions() of the last completed timestep        [8F + 5] heat   [8F + 6] status   [8F + 7] vflag
-//   [8F + 8]  cost of the last completed timestep (see the tier word)
+//   [8F + 8]  cost per timestep of the item (see the tier word)
 // Control record per WORLD (hints and statistics only; survives chunks and calls; a stale one costs a misprediction):
 //   [0] 2 = the classes below are a usable predictor   [1] [2] predictor class of every position coordinate (one byte
 //   each: 0 unchanged, 1 Point.move over TIME_DISC, 2 Point.move over the remainder of a timestep that fell back, 3
 //   unknown)   [3] consecutive rounds whose last accepted slot no move explains   [4] items of the current round that
-//   are finished (the last one commits)   statistics: [5] timesteps accepted  [6] timesteps evaluated  [7] rounds that
-//   accepted fewer slots than ran  [8] rounds without a predictor  [9] rounds
+//   are still out (the warp that finishes the last one commits)   statistics: [5] timesteps accepted  [6] timesteps
+//   evaluated  [7] rounds that accepted fewer slots than ran  [8] rounds without a predictor  [9] rounds   [10] 16 x the
+//   running estimate of the timesteps a round gets accepted (spec_shape)
 struct SpecParams {
     double *slots;
     long long *ctrl;
-    int S;                      // timesteps per world and round (K L ~ S)
-    int D;                      // cost per item the slot length aims at: L = clamp(D / cost of a timestep, 1, 16)
+    int S;                      // window (timesteps per round) of a world without history
+    int D;                      // cost per item the slot length aims at: L ~ D / cost of a timestep (spec_shape)
     int budget_cost;            // a world without a usable predictor: slot 0 alone, until it has cost this much
     int budget_steps;           // ... or made this many timesteps, per round
     int enabled;
+    // work queue of the rounds: tickets.  state[0] list length, [1] head (next ticket to consume), [2] tail (next ticket to
+    // produce), [3] worlds in flight.  Entry of ticket t, at queue[t % qcap]: (t + 1) << 25 | list entry << 5 | slot.
+    unsigned long long *queue, *state;
+    unsigned long long qcap;
+    // launches that only run when the list *gate points at is long / short (contact_kernel: runner bits 1, 2)
+    const unsigned long long *gate;
+    int abort_x4;               // a predicted slot is given up at abort_x4 / 4 times its expected cost
+    int nopred;                 // (debugging: never use a predictor)
     int round;                  // (debug statistics only)
-    unsigned long long *dbg;    // optional [rounds][4]: longest item (cycles), sum, items, items given up
+    unsigned long long *dbg;    // optional [chunks][4]: longest item (cycles), sum, items, items given up
 };
 constexpr int SPEC_K = 32;          // slots per list entry (stride of the item index; a world uses K <= SPEC_K of them)
-constexpr int SPEC_CTRL_WORDS = 10;
+constexpr int SPEC_CTRL_WORDS = 12;
 __host__ __device__ __forceinline__ int spec_slot_words(int F) { return 8 * F + 10; }
 // The tier word of a world: bits 0..7 scheduling tier, 8..31 check_collisions() of its last completed timestep, 32..55
 // COST of that timestep = the clock cycles the warp spent on it / 256 (about one call of the register-resident path).
 // Slot shape of a world for the spec rounds:
-__host__ __device__ __forceinline__ void spec_shape(long long tier_word, int S, int D, int &K, int &L) {
+// The WINDOW of a world (timesteps a round tries to cover) follows how far its predictions have been holding: a16 is 16 x
+// a running estimate of the timesteps a round gets accepted (control record [10]; 0 = no history: S).  Events -- the
+// trapped body reaching the other wall of its cage: one coordinate jumps, one velocity flips -- end a prediction; a world
+// with an event every 8 timesteps gets short windows of single-timestep slots, one with an event every 90 long ones.
+// L = timesteps per slot: D / cost (items of about D cost units), but at least window / SPEC_K; K = slots.
+__host__ __device__ __forceinline__ void spec_shape(long long tier_word, long long a16, int S, int D, int &K, int &L) {
     long long cost = (tier_word >> 32) & 0xffffff;
     if (cost < 1) cost = 1;
+    if (a16 <= 0) a16 = 16LL * S;
+    long long window = (3 * a16 + 31) / 32;                 // 1.5 x the estimate
+    window = window < 4 ? 4 : (window > 16 * SPEC_K ? 16 * SPEC_K : window);
+    const long long lmin = (window + SPEC_K - 1) / SPEC_K;
     long long l = D / cost;
-    L = (int)(l < 1 ? 1 : (l > 16 ? 16 : l));
-    K = (S + L - 1) / L;
+    l = l < lmin ? lmin : (l > 16 ? 16 : l);
+    L = (int)l;
+    K = (int)((window + l - 1) / l);
     if (K > SPEC_K) K = SPEC_K;
     if (K < 2) K = 2;
 }

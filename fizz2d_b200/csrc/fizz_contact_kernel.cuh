@@ -35,6 +35,7 @@ constexpr int CONTACT_BLOCK = CONTACT_WARPS * 32;
 __device__ unsigned long long g_dbg_cycles[65536];   // per world: cycles in ordinary (non-spec) items from timestep 2688 on
 #endif
 constexpr int SP_CAP = 160;       // survivor list capacity (>= MAX_PAIRS)
+#define FIZZ_SPEC_TIMEOUT_LOG2 32
 constexpr unsigned long long BULK_LIST = 16384;  // work lists this long are a throughput phase: the compact instance takes them
 constexpr long long FIZZ_ST_SPEC_ABORT = 100;    // internal: a spec item gave up (never leaves its slot record)
 
@@ -624,67 +625,122 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
     const long long Wp = kp.Wp;
     // (runner bits 1, 2: this launch only runs when the list is at least / less than BULK_LIST worlds long -- the host
     //  launches both instances on the same list and the one that suits its length does the work)
-    if (((runner & 2) && *count_ptr < BULK_LIST) || ((runner & 4) && *count_ptr >= BULK_LIST)) return;
-    // spec rounds (SpecParams, fizz_common.cuh): the items of a launch are (list entry, slot) pairs
+    {
+        const unsigned long long glen = sp.gate ? *sp.gate : *count_ptr;
+        if (((runner & 2) && glen < BULK_LIST) || ((runner & 4) && glen >= BULK_LIST)) return;
+    }
+    // spec rounds (SpecParams, fizz_common.cuh): the items of this launch come from the work queue of the rounds -- (list
+    // entry, slot) pairs -- not from the list
     const bool SPEC = FAST && sp.enabled != 0;
-    const int SK = SPEC ? SPEC_K : 1;
     const int SSW = spec_slot_words(F);
-    const unsigned long long count = min(*count_ptr, count_cap) * (unsigned long long)SK;  // (a capped list: classify_kernel's `cap`)
+    const unsigned long long count = SPEC ? 0ull : min(*count_ptr, count_cap);  // (a capped list: classify_kernel's `cap`)
     const bool speculate = (kp.trace == nullptr);  // the contact trace needs every trial's tuples: sequential then
+    // mutable per-world data: a spec launch re-reads what other SMs wrote earlier in the SAME launch -- past the L1
+    auto ldm = [&](const auto *p) { return SPEC ? __ldcg(p) : *p; };
+    // the clock as ONE value per warp: every decision taken on it (budgets of the spec items) must be warp-uniform, and
+    // the lanes of a warp do not read the same cycle
+    auto wclock = [&]() -> long long { return __shfl_sync(FULL, (long long)clock64(), 0); };
 
     // Work distribution: the first item of every warp is static (CTA c takes items 4c .. 4c+3), the rest is pulled from
     // the cursor.  A short list therefore keeps FEW CTAs resident (the others exit at once) instead of one warp in each:
     // the launches that run beside this one (spec rounds, the other instance) find room.
     bool first_item = true;
     for (;;) {
-        unsigned long long idx = 0;
-        if (first_item) {
-            idx = (unsigned long long)blockIdx.x * CONTACT_WARPS + warp;
-            first_item = false;
-        } else {
-            if (lane == 0) idx = (unsigned long long)gridDim.x * CONTACT_WARPS + atomicAdd(cursor, 1ULL);
-            idx = __shfl_sync(FULL, idx, 0);
+        unsigned long long idx = 0, wi = 0;
+        int slot = 0;
+        if constexpr (FAST) {
+            if (SPEC) {
+                // ---- next item of the rounds' queue: take a ticket, wait for its entry (or for the last world to finish) ----
+                unsigned long long e = ~0ull;
+                if (lane == 0) {
+                    const unsigned long long t = atomicAdd(sp.state + 1, 1ULL);
+                    volatile unsigned long long *qe = sp.queue + t % sp.qcap;
+                    volatile unsigned long long *active = sp.state + 3;
+                    const long long t_wait = clock64();
+                    for (;;) {
+                        const unsigned long long v = *qe;
+                        if ((v >> 25) == t + 1) { e = v; break; }
+                        if (*active == 0) break;
+                        // (safety net, never seen: two seconds without an item -- leave; the launch after the rounds brings
+                        //  every world to the chunk target anyway)
+                        if (clock64() - t_wait > (1LL << FIZZ_SPEC_TIMEOUT_LOG2)) break;
+                        __nanosleep(100);
+                    }
+                }
+                e = __shfl_sync(FULL, e, 0);
+                if (e == ~0ull) break;
+                __threadfence();                       // (the entry was published after the state it refers to)
+                wi = (e >> 5) & 0xfffffull;
+                slot = (int)(e & 31);
+            }
         }
-        if (idx >= count) break;
-        const unsigned long long wi = idx / (unsigned)SK;
-        const int slot = (int)(idx - wi * (unsigned)SK);
+        if (!SPEC) {
+            if (first_item) {
+                idx = (unsigned long long)blockIdx.x * CONTACT_WARPS + warp;
+                first_item = false;
+            } else {
+                if (lane == 0) idx = (unsigned long long)gridDim.x * CONTACT_WARPS + atomicAdd(cursor, 1ULL);
+                idx = __shfl_sync(FULL, idx, 0);
+            }
+            if (idx >= count) break;
+            wi = idx;
+        }
+        FIZZ_ASSERT(wi < min(*count_ptr, count_cap));
         const long long w = list[wi];
         FIZZ_ASSERT(w >= 0 && w < kp.W);
 
         // ---- load the world into the warp's shared-memory slice ------------------------------------------------
-        double heat = kp.heat[w];
-        long long step = kp.steps[w];
+        double heat = ldm(kp.heat + w);
+        long long step = ldm(kp.steps + w);
         long long target = kp.target_steps;          // where this item stops
-        // spec rounds: cost (fast-path calls + 10 x checks evaluated on the general path) at which the item stops at the next
-        // timestep boundary / is given up at once (only items that started from a PREDICTED state: a wrong prediction
-        // can be arbitrarily expensive to evaluate, and nobody needs its result)
+        // spec rounds: cost (units of 256 clock cycles) at which the item stops at the next timestep boundary / is given up
+        // at once (only items that started from a PREDICTED state: a wrong prediction can be arbitrarily expensive to
+        // evaluate, and nobody needs its result)
         const long long NOCAP = 0x3fffffffffffffffLL;
         long long call_budget = NOCAP, abort_cap = NOCAP;
-        const long long t_item = clock64();   // cost is measured: 256 clock cycles a unit (one fast-path call, roughly)
+        const long long t_item = wclock();   // cost is measured: 256 clock cycles a unit (one fast-path call, roughly)
         long long t_step = t_item;
         double *rec = nullptr;
         [[maybe_unused]] const double heat0 = heat;
-        // spec round: this item is done (or has nothing to do); the warp that finishes the LAST item of a world commits
-        // the round for it (fizz_spec.cuh)
+        // spec rounds: this item is done (or had nothing to do).  The warp that finishes the LAST item of a world's round
+        // commits the round (fizz_spec.cuh) and, unless the world is at the chunk target or has stopped, publishes the
+        // items of its next round: a world's rounds follow one another without waiting for any other world's.
         auto spec_item_done = [&]() {
             __threadfence();
             __syncwarp();
             long long old = 0;
-            long long *cnt = sp.ctrl + w * SPEC_CTRL_WORDS + 4;
-            if (lane == 0) old = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(cnt), 1ULL);
+            long long *pending = sp.ctrl + w * SPEC_CTRL_WORDS + 4;
+            if (lane == 0) old = (long long)atomicAdd(reinterpret_cast<unsigned long long *>(pending), ~0ULL);   // -1
             old = __shfl_sync(FULL, old, 0);
-            if (old == SPEC_K - 1) {
+            FIZZ_ASSERT(old >= 1 && old <= SPEC_K);
+            if (old == 1) {
                 __threadfence();
-                if (lane == 0) *cnt = 0;
-                spec_commit(kp, sp, w, sp.slots + wi * (unsigned)SPEC_K * (size_t)SSW, lane);
+                int knext = 0;
+                spec_commit(kp, sp, w, sp.slots + wi * (unsigned)SPEC_K * (size_t)SSW, lane, knext);
+                __syncwarp();
+                if (knext > 0) {
+                    unsigned long long base = 0;
+                    if (lane == 0) {
+                        atomicExch(reinterpret_cast<unsigned long long *>(pending), (unsigned long long)knext);
+                        __threadfence();
+                        base = atomicAdd(sp.state + 2, (unsigned long long)knext);
+                    }
+                    base = __shfl_sync(FULL, base, 0);
+                    __threadfence();
+                    if (lane < knext)
+                        __stcg(sp.queue + (base + lane) % sp.qcap, ((base + lane + 1) << 25) | (wi << 5) | (unsigned long long)lane);
+                } else if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(sp.state + 3, ~0ULL);     // one world less in flight; at 0 the idle warps leave
+                }
             }
             __syncwarp();
         };
         {
             double x = 0.0, y = 0.0, vx = 0.0, vy = 0.0;
             if (lane < F) {
-                x = kp.pos[(2 * lane) * Wp + w]; y = kp.pos[(2 * lane + 1) * Wp + w];
-                vx = kp.vel[(2 * lane) * Wp + w]; vy = kp.vel[(2 * lane + 1) * Wp + w];
+                x = ldm(kp.pos + (2 * lane) * Wp + w); y = ldm(kp.pos + (2 * lane + 1) * Wp + w);
+                vx = ldm(kp.vel + (2 * lane) * Wp + w); vy = ldm(kp.vel + (2 * lane + 1) * Wp + w);
             }
             bool skip = step >= kp.target_steps;
             // (a world that is at the target already -- listed by a reader that raced with another launch's write-back --
@@ -694,16 +750,15 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     // slot `slot` of this round: update() number step + slot * L ... of the world, from the PREDICTED state
                     const long long *ctrl = sp.ctrl + w * SPEC_CTRL_WORDS;
                     int Kw, Lw;
-                    spec_shape(kp.tier[w], sp.S, sp.D, Kw, Lw);
-                    const bool predictor = ctrl[0] > 1;
-                    // (ctrl[0] == -target: suspended for this chunk -- a timestep too long for a round, see below)
-                    skip = skip || step < 1 || kp.status[w] != 0 || slot >= (predictor ? Kw : 1) || ctrl[0] == -kp.target_steps;
+                    spec_shape(ldm(kp.tier + w), ldm(ctrl + 10), sp.S, sp.D, Kw, Lw);
+                    const bool predictor = ldm(ctrl) > 1;
+                    skip = skip || step < 1 || ldm(kp.status + w) != 0 || slot >= (predictor ? Kw : 1);
                     if (!skip && predictor) {
                         const long long my_start = step + (long long)slot * Lw;
                         if (my_start >= kp.target_steps) skip = true;
                         if (my_start + Lw < target) target = my_start + Lw;
                         if (!skip && lane < F && slot > 0) {
-                            const unsigned long long cw = (unsigned long long)ctrl[1 + (lane >> 2)];
+                            const unsigned long long cw = (unsigned long long)ldm(ctrl + 1 + (lane >> 2));
                             const int cx = (int)((cw >> (16 * (lane & 3))) & 255), cy = (int)((cw >> (16 * (lane & 3) + 8)) & 255);
                             const double rdt = kp.time_disc - dtk_all;
                             for (int t = slot * Lw; t > 0; t--) {
@@ -712,17 +767,16 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                             }
                         }
                         step = my_start;
-                        if (slot > 0) abort_cap = 2LL * sp.D + 64;
+                        // (abort_x4 / 4 times what the slot should cost by the world's own record, and never less than 2 D)
+                        if (slot > 0) {
+                            const long long expect = (long long)sp.abort_x4 * Lw * ((ldm(kp.tier + w) >> 32) & 0xffffff) / 4;
+                            abort_cap = (expect > 2LL * sp.D ? expect : 2LL * sp.D) + 32;
+                        }
                     } else if (!skip) {
                         // no usable predictor: this world advances sequentially, a bounded piece per round
                         if (step + sp.budget_steps < target) target = step + sp.budget_steps;
                         call_budget = sp.budget_cost;
                     }
-                    // slot 0 does real work, but a round ends with its longest item: a timestep that takes several times the
-                    // round's length (a resolve loop of thousands of passes: the worlds the watchdog is about to stop) is
-                    // given up as well -- the world is suspended until the launch after the rounds has brought it to the chunk
-                    // target, one warp, beside everybody else's leftovers
-                    if (slot == 0) abort_cap = 4LL * sp.D;
                     if (skip) { spec_item_done(); continue; }
                     rec = sp.slots + (wi * (unsigned)SPEC_K + (unsigned)slot) * (size_t)SSW;
                     if (lane < F) { rec[4 * lane] = x; rec[4 * lane + 1] = y; rec[4 * lane + 2] = vx; rec[4 * lane + 3] = vy; }
@@ -801,7 +855,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             ncalls++;
             ncalls_total++;
             if constexpr (FAST) {
-                if (abort_cap != NOCAP && ((clock64() - t_item) >> 8) > abort_cap) { status = FIZZ_ST_SPEC_ABORT; break; }
+                if (abort_cap != NOCAP && ((wclock() - t_item) >> 8) > abort_cap) { status = FIZZ_ST_SPEC_ABORT; break; }
             }
 
             int nh = 0;
@@ -1187,7 +1241,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     const int nb = kp.nv[b];
                     int ret = TRAP_MIDSTEP, steps_here = 0;
                     // (one instantiation for triangles and quadrilaterals; anything else stays on the general path)
-                    const long long t_call = clock64();
+                    const long long t_call = wclock();
                     const long long cost_now = (t_call - t_item) >> 8;
                     if (nb == 3 || nb == 4)
                         ret = trapped_run<FAST>(s, kp, F, X, lane, b, heat, ncalls, ncalls_total, step, k, dt, steps_here,
@@ -1197,13 +1251,13 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     if (steps_here) {
                         // whole timesteps went by in registers: all of them trapped ones
                         trapped = true; calm = 0; quiet = 0; quiet_empty = 0; fast_step = 0;
-                        t_step = clock64();
+                        t_step = wclock();
                         last_cost = (int)(((t_step - t_call) >> 8) / steps_here);
                     }
                     if (ret == TRAP_BOUNDARY) {
                         // a fresh update() (or the target): the vertices are derived state again
                         resolve = false; verts_explicit = false;
-                        if (step >= target || (call_budget != NOCAP && ((clock64() - t_item) >> 8) >= call_budget)) break;
+                        if (step >= target || (call_budget != NOCAP && ((wclock() - t_item) >> 8) >= call_budget)) break;
                         continue;
                     }
                     verts_explicit = true;
@@ -1233,7 +1287,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
             step++;                                            // :259
             last_calls = ncalls;
             {
-                const long long now = clock64();
+                const long long now = wclock();
                 last_cost = (int)((now - t_step) >> 8);
                 t_step = now;
             }
@@ -1249,7 +1303,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 fast_step = 0;
                 if (heavy) trapped = true;  // flagged for the NEXT chunk; this chunk is finished here (no idle time)
             }
-            if (step >= target || (call_budget != NOCAP && ((clock64() - t_item) >> 8) >= call_budget)) break;
+            if (step >= target || (call_budget != NOCAP && ((wclock() - t_item) >> 8) >= call_budget)) break;
             verts_explicit = false;
         }
 
@@ -1267,7 +1321,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                 if (status == 0 && !__all_sync(FULL, fin)) status = FIZZ_ST_NONFINITE;
                 // slot 0 started from the real state: whatever it found is the world's (the vertices of a timestep that
                 // ended in a resolve pass are explicit state, written where a normal launch writes them)
-                if (slot == 0 && verts_explicit && status != FIZZ_ST_SPEC_ABORT)
+                if (slot == 0 && verts_explicit)
                     for (int r = lane; r < 2 * V; r += 32) kp.verts[(size_t)r * Wp + w] = s.vert[r];
                 if (lane == 0) {
                     const bool clean = status == 0 && !verts_explicit &&
@@ -1276,7 +1330,7 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
                     m[1] = step - step_in; m[2] = ncalls_total; m[3] = fast_calls; m[4] = last_calls;
                     rec[8 * F + 5] = heat; m[6] = status; m[7] = verts_explicit ? 1 : 0;
                     m[8] = ((clock64() - t_item) >> 8) / (step > step_in ? step - step_in : 1);   // cost per timestep of this item
-                    m[0] = 1 | (clean ? 2 : 0) | (status == FIZZ_ST_SPEC_ABORT ? 4 : 0);
+                    m[0] = 1 | (clean ? 2 : 0);
                     if (sp.dbg) {
                         const unsigned long long cyc = (unsigned long long)(clock64() - t_item);
                         atomicMax(sp.dbg + 4 * sp.round, cyc);
@@ -1345,7 +1399,9 @@ contact_kernel(const __grid_constant__ KParams kp, const long long *__restrict__
 __global__ void classify_kernel(const long long *status, const long long *steps, long long *tier, long long W,
                                 long long target, long long tier_lo, long long tier_hi, int use_rate,
                                 long long rate_lo, long long rate_hi, long long *list, unsigned long long *count,
-                                long long mark = -1, unsigned long long cap = ~0ull, int flagmode = 0) {
+                                long long mark = -1, unsigned long long cap = ~0ull, int flagmode = 0,
+                                const unsigned long long *gate = nullptr) {
+    if (gate && *gate >= BULK_LIST) return;      // (a throughput phase: no spec rounds, see fizz_step)
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long tw = 0;
     bool lag = false;
@@ -1379,6 +1435,30 @@ __global__ void classify_kernel(const long long *status, const long long *steps,
 __global__ void release_kernel(long long *tier, long long W) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w < W && (tier[w] & 255) == 4) tier[w] = (tier[w] & ~255LL) | 3;
+}
+
+// Spec rounds of a chunk, start: every listed world gets the items of its first round (fizz_common.cuh: SpecParams).
+__global__ void spec_reset_kernel(SpecParams sp) {
+    // tickets taken by warps that left when the last chunk's rounds ended were never produced: skip them
+    if (sp.state[1] > sp.state[2]) sp.state[2] = sp.state[1];
+    sp.state[3] = 0;
+}
+__global__ void spec_seed_kernel(const __grid_constant__ KParams kp, SpecParams sp, const long long *__restrict__ list,
+                                 unsigned long long cap) {
+    const unsigned long long n = min(sp.state[0], cap);
+    const unsigned long long wi = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= n) return;
+    const long long w = list[wi];
+    long long *ctrl = sp.ctrl + w * SPEC_CTRL_WORDS;
+    if (kp.steps[w] >= kp.target_steps || kp.steps[w] < 1 || kp.status[w] != 0) return;
+    int Kw, Lw;
+    spec_shape(kp.tier[w], ctrl[10], sp.S, sp.D, Kw, Lw);
+    const int k = ctrl[0] > 1 ? Kw : 1;
+    ctrl[4] = k;
+    atomicAdd(sp.state + 3, 1ULL);
+    const unsigned long long base = atomicAdd(sp.state + 2, (unsigned long long)k);
+    for (int i = 0; i < k; i++)
+        sp.queue[(base + i) % sp.qcap] = ((base + i + 1) << 25) | (wi << 5) | (unsigned long long)i;
 }
 
 // Derived vertices for worlds whose point.pos are not explicit state: |r|cos(phi) + com.x, |r|sin(phi) + com.y

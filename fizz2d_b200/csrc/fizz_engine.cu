@@ -5,9 +5,13 @@
 //     only, advances quiescent steps and stops a world at the first non-empty broad phase; (2) classify_kernel
 //     builds the list of worlds short of the chunk target; (3) contact_kernel -- persistent, warp per world,
 //     cooperative SAT / resolution -- brings those worlds to the chunk target.  No host synchronisation.
-//     Worlds found trapped and heavy leave this pipeline at a chunk boundary: "runner" launches of the contact kernel
-//     on library-owned streams step them to the end of the fizz_step() call (see fizz_step).
-//   FIZZ_MODE_HYBRID_SYNC: the same without runner launches.
+//     Calls of >= 128 timesteps: in every chunk whose work list is short (the scene has calmed down), the worlds whose
+//     timesteps are expensive -- trapped bodies: hundreds of resolve passes per timestep, forever -- are stepped
+//     TIME-PARALLEL by the "spec rounds" (fizz_common.cuh: SpecParams; $FIZZ_SPEC=0 turns them off): K warps evaluate K
+//     consecutive pieces of a world's future from predicted start states, a prediction is accepted only if it equals the
+//     real state bit for bit.  The few expensive worlds no predictor fits leave the pipeline at a chunk boundary: "runner"
+//     launches of the contact kernel on library-owned streams step them to the end of the fizz_step() call.
+//   FIZZ_MODE_HYBRID_SYNC: the plain chunk pipeline (no spec rounds, no runner launches).
 //   FIZZ_MODE_HYBRID3: adds the separation-prover tier and runs two contact-kernel instances side by side.
 //   FIZZ_MODE_THREAD: step_kernel<F, double> -- thread per world, full semantics in one launch.
 //   FIZZ_MODE_THREAD_FP32: step_kernel<F, float> -- the same operation sequence in single precision (optional mode).
@@ -197,15 +201,17 @@ struct FizzGroup {
     unsigned long long *rcount;  // [NR][2] count, cursor
     // spec rounds (fizz_common.cuh: SpecParams): time-parallel stepping of the heavy trapped worlds, chunk by chunk
     bool spec_on;
-    int spec_S, spec_D, spec_cost, spec_budget, spec_slack;
+    int spec_S, spec_D, spec_cost, spec_budget;
     long long scap;              // entries of the spec list
     long long *spec_list;        // [scap]                       (all of it allocated on first use)
     double *spec_slots;          // [scap][SPEC_K][slot words]
     long long *spec_ctrl;        // [W][SPEC_CTRL_WORDS]
-    unsigned long long *spec_count;   // [0] list length, [1 + r] work cursor of round r of the current fizz_step() call
+    unsigned long long *spec_state;   // [0] list length, [1] [2] [3] the rounds' queue: head, tail, worlds in flight, [4] unused cursor
+    unsigned long long *spec_queue;   // [scap * SPEC_K] tickets
+    int spec_ctas;                    // CTAs per SM of the rounds' launch
     cudaStream_t spec_stream;
     cudaEvent_t spec_fork, spec_join;
-    static const int SPEC_RMAX = 4096;
+    static const int SPEC_RMAX = 64;     // (debug statistics: chunks)
     unsigned long long *sched_count;  // [0] = count, [1] = cursor
     unsigned char *vbody_dev;
     // optional per-kernel timing (fizz_set_profiling)
@@ -328,7 +334,7 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
     g->profile = false; g->ev_used = 0; g->prof_error = cudaSuccess;
     g->side = nullptr; g->ev_fork = nullptr; g->ev_join = nullptr;
     g->rlist = nullptr; g->rcount = nullptr;
-    g->spec_list = nullptr; g->spec_slots = nullptr; g->spec_ctrl = nullptr; g->spec_count = nullptr;
+    g->spec_list = nullptr; g->spec_slots = nullptr; g->spec_ctrl = nullptr; g->spec_state = nullptr; g->spec_queue = nullptr;
     g->spec_stream = nullptr; g->spec_fork = nullptr; g->spec_join = nullptr;
     {
         auto env_int = [](const char *name, long long dflt, long long lo, long long hi) {
@@ -338,11 +344,11 @@ int fizz_group_create(const FizzGroupDesc *d, int64_t n_worlds, int device, void
             return x < lo ? lo : (x > hi ? hi : x);
         };
         g->spec_on = env_int("FIZZ_SPEC", 1, 0, 1) != 0;
-        g->spec_S = (int)env_int("FIZZ_SPEC_S", 32, 2, 512);          // timesteps per world and round
-        g->spec_D = (int)env_int("FIZZ_SPEC_D", 700, 1, 1 << 20);     // cost per item (~0.13 us per unit)
+        g->spec_S = (int)env_int("FIZZ_SPEC_S", 32, 2, 512);          // window of a world without history (timesteps)
+        g->spec_D = (int)env_int("FIZZ_SPEC_D", 200, 1, 1 << 20);     // cost per item (~0.13 us per unit)
         g->spec_cost = (int)env_int("FIZZ_SPEC_COST", 48, 1, 1 << 20);  // worlds at least this costly per timestep
         g->spec_budget = (int)env_int("FIZZ_SPEC_BUDGET", 0, 0, 1 << 30);   // 0: D
-        g->spec_slack = (int)env_int("FIZZ_SPEC_SLACK", 8, 4, 64);    // rounds = slack/4 x the rounds of a perfect predictor
+        g->spec_ctas = (int)env_int("FIZZ_SPEC_CTAS", 2, 1, 3);       // CTAs per SM of the rounds' launch
         g->scap = env_int("FIZZ_SPEC_CAP", 4096, 1, 1 << 20);
         if (g->scap > n_worlds) g->scap = n_worlds;
     }
@@ -489,7 +495,8 @@ int fizz_group_destroy(FizzGroup *g) {
         if (g->spec_list) cudaFree(g->spec_list);
         if (g->spec_slots) cudaFree(g->spec_slots);
         if (g->spec_ctrl) cudaFree(g->spec_ctrl);
-        if (g->spec_count) cudaFree(g->spec_count);
+        if (g->spec_state) cudaFree(g->spec_state);
+        if (g->spec_queue) cudaFree(g->spec_queue);
         if (g->spec_fork) cudaEventDestroy(g->spec_fork);
         if (g->spec_join) cudaEventDestroy(g->spec_join);
         if (g->spec_stream) cudaStreamDestroy(g->spec_stream);
@@ -642,11 +649,11 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
     cudaEventCreate(&d0);
     cudaEventRecord(d0, st);
 #endif
-    // spec rounds (FIZZ_MODE_HYBRID, calls of >= 128 timesteps): in every chunk after the first, the trapped worlds whose
+    // spec rounds (FIZZ_MODE_HYBRID, calls of >= 128 timesteps): in every chunk after the first, the worlds whose
     // timesteps are expensive are brought to the chunk target time-parallel (fizz_common.cuh: SpecParams) on a library-owned
     // stream, beside the launch that steps everything else; whatever the rounds leave is finished by a launch after the
-    // join.  Not with the contact trace on (its records would come from discarded slots too).  With spec rounds there are
-    // no runner launches: no world's chain is long enough to be worth skipping the chunk boundaries for.
+    // join.  Not with the contact trace on (its records would come from discarded slots too).  With spec rounds the
+    // runner launches only take the expensive worlds the rounds cannot predict.
     const bool spec = (g->mode == FIZZ_MODE_HYBRID) && n_steps >= 128 && g->spec_on && kp.trace == nullptr;
     const bool runners = (g->mode == FIZZ_MODE_HYBRID) && n_steps >= 128;
     const SpecParams no_spec = {};
@@ -659,7 +666,10 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             CU(cudaMalloc(&g->spec_list, sizeof(long long) * (size_t)g->scap));
             CU(cudaMalloc(&g->spec_slots, sizeof(double) * slot_words));
             CU(cudaMalloc(&g->spec_ctrl, sizeof(long long) * ctrl_words));
-            CU(cudaMalloc(&g->spec_count, sizeof(unsigned long long) * (1 + FizzGroup::SPEC_RMAX)));
+            CU(cudaMalloc(&g->spec_state, sizeof(unsigned long long) * 8));
+            CU(cudaMalloc(&g->spec_queue, sizeof(unsigned long long) * (size_t)g->scap * SPEC_K));
+            CU(cudaMemset(g->spec_state, 0, sizeof(unsigned long long) * 8));
+            CU(cudaMemset(g->spec_queue, 0, sizeof(unsigned long long) * (size_t)g->scap * SPEC_K));
             CU(cudaMemset(g->spec_slots, 0, sizeof(double) * slot_words));
             CU(cudaMemset(g->spec_ctrl, 0, sizeof(long long) * ctrl_words));
             CU(cudaStreamCreateWithFlags(&g->spec_stream, cudaStreamNonBlocking));
@@ -668,7 +678,9 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
         }
         sp.slots = g->spec_slots; sp.ctrl = g->spec_ctrl;
         sp.S = g->spec_S; sp.D = g->spec_D; sp.budget_cost = g->spec_budget > 0 ? g->spec_budget : g->spec_D; sp.budget_steps = 32; sp.enabled = 1;
-        CU(cudaMemsetAsync(g->spec_count, 0, sizeof(unsigned long long) * (1 + FizzGroup::SPEC_RMAX), st));
+        { const char *v = std::getenv("FIZZ_SPEC_ABORT_X4"); sp.abort_x4 = (v && *v) ? std::atoi(v) : 12; if (sp.abort_x4 < 4) sp.abort_x4 = 4; }
+        { const char *v = std::getenv("FIZZ_SPEC_NOPRED"); sp.nopred = (v && *v == '1') ? 1 : 0; }
+        sp.queue = g->spec_queue; sp.state = g->spec_state; sp.qcap = (unsigned long long)g->scap * SPEC_K;
     }
     bool rused[FizzGroup::NR] = {};
     int rnext = 0;
@@ -740,78 +752,77 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                 rused[slot] = true;
                 g->launches += 2;
             }
-            // latency-tuned: ONE instance (two narrow-phase items per lane, 3 CTAs/SM) steps every lagging world, so the
-            // world with the longest chain of resolve passes never waits for anything
-            // (work list in world order: measured -- grouping the trapped worlds at the head of the list, or sorting them
-            //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
-            bool spec_chunk = false;
             if (spec && g->target > c) {
-                // rounds for this chunk: enough for a world that is predicted right half of the time
-                long long rounds = ((long long)c * g->spec_slack / 4 + g->spec_S - 1) / g->spec_S + 2;
-                if (spec_round + rounds > FizzGroup::SPEC_RMAX) rounds = FizzGroup::SPEC_RMAX - spec_round;
-                if (rounds > 0) {
-                    spec_chunk = true;
-                    // the trapped worlds whose last timestep cost >= spec_cost (list in world order, rebuilt every chunk: a
-                    // world leaves when its contact ends); a listed world is left alone by the launch beside the rounds
-                    CU(cudaMemsetAsync(g->spec_count, 0, sizeof(unsigned long long), st));
-                    classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 2, g->spec_cost,
-                                                           1LL << 40, g->spec_list, g->spec_count, -1,
-                                                           (unsigned long long)g->scap, 1);
-                    // everything else that lags (same selection, complemented) -- listed BEFORE the rounds start: their
-                    // commit steps rewrite the tier words this selection reads
-                    classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 2, 0, g->spec_cost,
-                                                           g->sched_list, g->sched_count, -1, ~0ull, 2);
-                    CU(cudaEventRecord(g->spec_fork, st));
-                    CU(cudaStreamWaitEvent(g->spec_stream, g->spec_fork, 0));
-                    const long long sneed = g->scap * SPEC_K / CONTACT_WARPS;
-                    const dim3 sgrid((unsigned)(sneed < tfull ? sneed : tfull));
-                    for (long long r = 0; r < rounds; r++, spec_round++) {
-#ifdef FIZZ_RUNNER_DEBUG
-                        sp.round = (int)spec_round; sp.dbg = d_sdbg;
-                        if (nchunk < 64) d_round0[nchunk + 1] = spec_round + 1;
-#endif
-                        contact_kernel<true><<<sgrid, CONTACT_BLOCK, g->contact_smem, g->spec_stream>>>(
-                            kp, g->spec_list, g->spec_count, g->spec_count + 1 + spec_round, (unsigned long long)g->scap, 0, sp);
-                    }
-                    CU(cudaEventRecord(g->spec_join, g->spec_stream));
-#ifdef FIZZ_RUNNER_DEBUG
-                    if (nchunk < 64) { cudaEventCreate(&d_spec[nchunk]); cudaEventRecord(d_spec[nchunk], g->spec_stream); }
-#endif
-                    g->launches += rounds + 1;
-                }
-            }
-            if (!spec_chunk) {
+                // ---- a chunk with spec rounds ----------------------------------------------------------------------------
+                // (1) everything that lags; its length decides, ON THE DEVICE, which of the launches below do the work:
+                //     a long list (>= BULK_LIST: the scene stays busy for the first few hundred timesteps) is a throughput
+                //     phase -- the compact high-occupancy instance steps all of it, there are no rounds;
+                unsigned long long *all_count = g->sched_count + 2;
                 classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
-                                                       g->sched_list, g->sched_count);   // (tier 4: owned by a runner)
-            }
-            // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
-            // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
-            if (g->target == c) {
-                contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                     g->sched_count + 1, ~0ull, 0, no_spec);
-            } else if (spec) {
-                // with the expensive worlds in the spec rounds, a long list is a throughput phase again (the scene stays
-                // busy for a few hundred timesteps): both instances are launched, the one the list length suits runs
-                contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                     g->sched_count + 1, ~0ull, 2, no_spec);
-                contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
-                                                                                    g->sched_count + 1, ~0ull, 4, no_spec);
-                g->launches++;
-            } else {
+                                                       g->sched_list2, all_count);
+                contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list2, all_count,
+                                                                                     g->sched_count + 3, ~0ull, 2, no_spec);
+                // (2) otherwise: the worlds whose timesteps cost >= spec_cost and that the rounds can predict (list in world
+                //     order, rebuilt every chunk) go through the rounds, on the library's spec stream; everything else that
+                //     lags is stepped beside them by the latency-tuned instance.  Both lists are made BEFORE the rounds start:
+                //     their commit steps rewrite the tier words the selection reads
+                CU(cudaMemsetAsync(g->spec_state, 0, sizeof(unsigned long long), st));
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 2, g->spec_cost,
+                                                       1LL << 40, g->spec_list, g->spec_state, -1, (unsigned long long)g->scap, 1,
+                                                       all_count);
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 2, 0, g->spec_cost,
+                                                       g->sched_list, g->sched_count, -1, ~0ull, 2, all_count);
+                CU(cudaEventRecord(g->spec_fork, st));
+                CU(cudaStreamWaitEvent(g->spec_stream, g->spec_fork, 0));
+#ifdef FIZZ_RUNNER_DEBUG
+                sp.round = (int)(nchunk < 64 ? nchunk : 63); sp.dbg = d_sdbg;
+                if (nchunk < 64) d_round0[nchunk + 1] = nchunk + 1;
+#endif
+                spec_reset_kernel<<<1, 1, 0, g->spec_stream>>>(sp);
+                spec_seed_kernel<<<(unsigned)((g->scap + 127) / 128), 128, 0, g->spec_stream>>>(kp, sp, g->spec_list,
+                                                                                                 (unsigned long long)g->scap);
+                // one launch per chunk: the warps take (world, slot) items from the rounds' queue until every listed world
+                // is at the chunk target; it leaves room on every SM for the launch beside it
+                const dim3 sgrid((unsigned)(g->sm_count * g->spec_ctas));
+                contact_kernel<true><<<sgrid, CONTACT_BLOCK, g->contact_smem, g->spec_stream>>>(
+                    kp, g->spec_list, g->spec_state, g->spec_state + 4, (unsigned long long)g->scap, 0, sp);
+                CU(cudaEventRecord(g->spec_join, g->spec_stream));
+#ifdef FIZZ_RUNNER_DEBUG
+                if (nchunk < 64) { cudaEventCreate(&d_spec[nchunk]); cudaEventRecord(d_spec[nchunk], g->spec_stream); }
+#endif
+                spec_round++;
                 contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
                                                                                     g->sched_count + 1, ~0ull, 0, no_spec);
-            }
 #ifdef FIZZ_RUNNER_DEBUG
-            if (nchunk < 64) { cudaEventCreate(&d_main[nchunk]); cudaEventRecord(d_main[nchunk], st); }
+                if (nchunk < 64) { cudaEventCreate(&d_main[nchunk]); cudaEventRecord(d_main[nchunk], st); }
 #endif
-            if (spec_chunk) {
-                // join, then whatever the rounds left short of the chunk target (and worlds beyond the list's capacity)
+                // (3) join, then whatever is still short of the chunk target: worlds that turned out unpredictable during
+                //     the rounds, worlds beyond the spec list's capacity
                 CU(cudaStreamWaitEvent(st, g->spec_join, 0));
+                CU(cudaMemsetAsync(all_count, 0, 2 * sizeof(unsigned long long), st));
                 classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
-                                                       g->sched_list2, g->sched_count + 2);
-                contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list2, g->sched_count + 2,
+                                                       g->sched_list2, all_count);
+                contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list2, all_count,
                                                                                     g->sched_count + 3, ~0ull, 0, no_spec);
-                g->launches += 4;
+                g->launches += 11;
+            } else {
+                // latency-tuned: ONE instance (two narrow-phase items per lane, 3 CTAs/SM) steps every lagging world, so the
+                // world with the longest chain of resolve passes never waits for anything
+                // (work list in world order: measured -- grouping the trapped worlds at the head of the list, or sorting them
+                //  by call rate, puts the longest chains on the same SMs and costs 2-5 % of a pass)
+                classify_kernel<<<cgrid, 256, 0, st>>>(kp.status, kp.steps, kp.tier, W, g->target, 0, 3, 0, 0, 1,
+                                                       g->sched_list, g->sched_count);   // (tier 4: owned by a runner)
+                // the chunk that starts at step 0 has every world in the scene and none trapped yet: a pure throughput
+                // phase, which the compact high-occupancy instance handles ~20 % faster; afterwards latency rules
+                if (g->target == c)
+                    contact_kernel<false><<<kgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                         g->sched_count + 1, ~0ull, 0, no_spec);
+                else
+                    contact_kernel<true><<<tgrid, CONTACT_BLOCK, g->contact_smem, st>>>(kp, g->sched_list, g->sched_count,
+                                                                                        g->sched_count + 1, ~0ull, 0, no_spec);
+#ifdef FIZZ_RUNNER_DEBUG
+                if (nchunk < 64) { cudaEventCreate(&d_main[nchunk]); cudaEventRecord(d_main[nchunk], st); }
+#endif
             }
             g->launches -= 2;
         } else {
@@ -846,7 +857,7 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             cudaEventCreate(&d_chunk[nchunk]); cudaEventRecord(d_chunk[nchunk], st); d_len[nchunk] = c;
             cudaMemcpyAsync(d_cnt[nchunk], kp.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
             cudaMemcpyAsync(&d_cnt[nchunk][4], g->sched_count, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-            if (spec) cudaMemcpyAsync(&d_cnt[nchunk][8], g->spec_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            if (spec) cudaMemcpyAsync(&d_cnt[nchunk][8], g->spec_state, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         }
 #endif
     }
@@ -940,11 +951,11 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
                 std::vector<long long> idx;
                 for (long long w = 0; w < W; w++) if (c[w * SPEC_CTRL_WORDS + 9]) idx.push_back(w);
                 std::sort(idx.begin(), idx.end(), [&](long long a, long long b) {
-                    return c[a * SPEC_CTRL_WORDS + 9] - c[a * SPEC_CTRL_WORDS + 5] / 32 > c[b * SPEC_CTRL_WORDS + 9] - c[b * SPEC_CTRL_WORDS + 5] / 32; });
+                    return c[a * SPEC_CTRL_WORDS + 9] > c[b * SPEC_CTRL_WORDS + 9]; });
                 fprintf(stderr, "\n  worst worlds (rounds - accepted/32): world rounds accepted evaluated mispredicted blind | calls cost tier | classes");
                 for (size_t i = 0; i < idx.size() && i < 16; i++) {
                     const long long *x = c.data() + idx[i] * SPEC_CTRL_WORDS;
-                    fprintf(stderr, "\n   %lld: %lld %lld %lld %lld %lld | %lld %lld %lld | %016llx %016llx", idx[i], x[9], x[5], x[6], x[7], x[8],
+                    fprintf(stderr, "\n   %lld: (window estimate %lld) %lld %lld %lld %lld %lld | %lld %lld %lld | %016llx %016llx", idx[i], x[10] / 16, x[9], x[5], x[6], x[7], x[8],
                             (tw[idx[i]] >> 8) & 0xffffff, (tw[idx[i]] >> 32) & 0xffffff, tw[idx[i]] & 255, (unsigned long long)x[1], (unsigned long long)x[2]);
                 }
             }
@@ -1063,6 +1074,26 @@ int fizz_counters(FizzGroup *g, int64_t *out4, int32_t reset, void *stream) {
     CU(cudaMemcpyAsync(out4, g->kp.counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (reset) CU(cudaMemsetAsync(g->kp.counters, 0, 4 * sizeof(int64_t), st));
+    return FIZZ_OK;
+}
+
+int fizz_set_spec(FizzGroup *g, int32_t enabled, int32_t window0, int32_t slot_cost, int32_t min_cost) {
+    if (!g) return fail(FIZZ_E_ARG, "fizz_set_spec: null group");
+    if (window0 > 512) return fail(FIZZ_E_ARG, "fizz_set_spec: window0 must be <= 512");
+    if (enabled >= 0) g->spec_on = enabled != 0;
+    if (window0 > 0) g->spec_S = window0 < 2 ? 2 : window0;
+    if (slot_cost > 0) g->spec_D = slot_cost;
+    if (min_cost > 0) g->spec_cost = min_cost;
+    return FIZZ_OK;
+}
+
+int fizz_spec_stats(FizzGroup *g, int64_t *out4, int32_t reset, void *stream) {
+    if (!g || !out4) return fail(FIZZ_E_ARG, "fizz_spec_stats: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(g->device));
+    CU(cudaMemcpyAsync(out4, g->kp.counters + 4, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (reset) CU(cudaMemsetAsync(g->kp.counters + 4, 0, 4 * sizeof(int64_t), st));
     return FIZZ_OK;
 }
 

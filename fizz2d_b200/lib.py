@@ -69,6 +69,8 @@ EXPORTS = {
     "fizz_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "fizz_vertices": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fizz_counters": (C.c_int, [C.c_void_p, lp, C.c_int32, C.c_void_p]),
+    "fizz_set_spec": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "fizz_spec_stats": (C.c_int, [C.c_void_p, lp, C.c_int32, C.c_void_p]),
     "fizz_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "fizz_profile_read": (C.c_int, [C.c_void_p, dp, lp, C.c_int32]),
     "fizz_fp64_peak": (C.c_int, [C.c_int, C.c_int32, dp, dp]),

@@ -234,6 +234,20 @@ int fizz_profile_read(FizzGroup *g, double *ms3, int64_t *launches3, int32_t res
  * by the contact kernel, [3] of those inside its single-contact fast path.  Thread mode does not count. */
 int fizz_counters(FizzGroup *g, int64_t *out4, int32_t reset, void *stream);
 
+/* Spec rounds (mode FIZZ_MODE_HYBRID, calls of >= 128 timesteps, contact trace off): expensive worlds -- a trapped body
+ * makes hundreds of resolve passes per timestep, forever -- are stepped TIME-PARALLEL: K warps evaluate K consecutive
+ * pieces of one world's future from predicted start states, and a piece is accepted only if the state it started from
+ * equals, bit for bit, the state the piece before it ended in.  Results never depend on any of these settings (a wrong
+ * prediction is thrown away and evaluated again); they trade latency of the longest chains against wasted evaluations.
+ * enabled: 0 off, 1 on, < 0 keep (default on; $FIZZ_SPEC=0 at group creation turns it off).  The others, <= 0 keep:
+ * window0 = timesteps a round of a world without history tries to cover (32); slot_cost = cost a slot aims at, in units
+ * of 256 clock cycles of one warp (200); min_cost = cost per timestep from which a world takes part (48). */
+int fizz_set_spec(FizzGroup *g, int32_t enabled, int32_t window0, int32_t slot_cost, int32_t min_cost);
+
+/* What the spec rounds did since the last reset (synchronises `stream`): out4[0] timesteps accepted, [1] timesteps
+ * evaluated (accepted + thrown away), [2] rounds committed, [3] rounds that threw at least one slot away. */
+int fizz_spec_stats(FizzGroup *g, int64_t *out4, int32_t reset, void *stream);
+
 /* FP64 FMA throughput microbenchmark (the roofline denominator MEASURED_PEAKS.json lacks): runs `iters`
  * dependent-chain DFMA rounds on every SM of `device` and returns achieved TFLOP/s (FMA = 2 flops). */
 int fizz_fp64_peak(int device, int32_t iters, double *tflops, double *ms);
