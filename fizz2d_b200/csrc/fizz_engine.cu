@@ -668,10 +668,12 @@ int fizz_step(FizzGroup *g, int64_t n_steps, void *stream) {
             CU(cudaMalloc(&g->spec_ctrl, sizeof(long long) * ctrl_words));
             CU(cudaMalloc(&g->spec_state, sizeof(unsigned long long) * 8));
             CU(cudaMalloc(&g->spec_queue, sizeof(unsigned long long) * (size_t)g->scap * SPEC_K));
-            CU(cudaMemset(g->spec_state, 0, sizeof(unsigned long long) * 8));
-            CU(cudaMemset(g->spec_queue, 0, sizeof(unsigned long long) * (size_t)g->scap * SPEC_K));
-            CU(cudaMemset(g->spec_slots, 0, sizeof(double) * slot_words));
-            CU(cudaMemset(g->spec_ctrl, 0, sizeof(long long) * ctrl_words));
+            // (on the caller's stream: everything that touches these buffers is ordered after it through the fork events;
+            //  a plain cudaMemset runs on the legacy default stream, which the non-blocking streams do not wait for)
+            CU(cudaMemsetAsync(g->spec_state, 0, sizeof(unsigned long long) * 8, st));
+            CU(cudaMemsetAsync(g->spec_queue, 0, sizeof(unsigned long long) * (size_t)g->scap * SPEC_K, st));
+            CU(cudaMemsetAsync(g->spec_slots, 0, sizeof(double) * slot_words, st));
+            CU(cudaMemsetAsync(g->spec_ctrl, 0, sizeof(long long) * ctrl_words, st));
             CU(cudaStreamCreateWithFlags(&g->spec_stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&g->spec_fork, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&g->spec_join, cudaEventDisableTiming));
