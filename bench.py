@@ -40,8 +40,10 @@ UNIT = "world-steps/s"
 CONFIGS = {
     2: dict(kind="scene", scenes=["BOX_1SQUAREFRICTION"], worlds=4096, timesteps=1000, seed=20260002,
             mode="hybrid", chunk=256, label="BASELINE config 2"),
+    # (spec: tuning of the time-parallel spec rounds, DESIGN.md 5d, like `chunk` a schedule knob that cannot change a
+    #  result -- worlds take part from a cost of 100 units per timestep (library default 48): measured 258 -> 237 ms per pass)
     3: dict(kind="scene", scenes=["RAMPWORLD_2TRIANGLES_5SQUARES"], worlds=65536, timesteps=10000, seed=20260003,
-            mode="hybrid", chunk=96, label="BASELINE config 3"),
+            mode="hybrid", chunk=96, spec=dict(min_cost=100), label="BASELINE config 3"),
     4: dict(kind="mixed", scenes=["2CHAMBERS_3BALLS", "STACKEDCHAMBERS_1SQUARE"], worlds=262144, timesteps=1000,
             seed=20260004, mode="hybrid3", chunk=32, label="BASELINE config 4"),
     5: dict(kind="ga", scenes=["PENTAGONVOID_1SQUARE"], worlds=131072, timesteps=2000, seed=20260005,
@@ -340,6 +342,9 @@ class Bench:
         self.specs = specs
         self.bw = fz.BatchedWorld(specs, ids, device=local_rank)
         self.bw.set_tuning(mode, chunk)
+        self.spec_tuning = dict(CONFIGS[config_id].get("spec") or {}) if mode == "hybrid" else {}
+        if self.spec_tuning:
+            self.bw.set_spec(**self.spec_tuning)
         self.W = self.bw.n_worlds
         self.d2h_bytes = 8 * self.W * (4 + 1 + 1)
         self.state0 = self.bw.snapshot()
@@ -624,7 +629,8 @@ def run_gpu(args):
                 "worlds": {"running": int((status == 0).sum()), "capped": int((status == 1).sum()),
                            "other": int((status > 1).sum()), "world_steps_per_pass": m["world_steps"],
                            "check_collisions_per_world_step": float(calls.sum()) / max(1, m["world_steps"])},
-                "mode": args.mode, "chunk_steps": args.chunk, "source_id": source_id()}
+                "mode": args.mode, "chunk_steps": args.chunk, "spec_rounds_tuning": b.spec_tuning or "library defaults",
+                "source_id": source_id()}
         if gather_ms is not None:
             line["gather"] = {"ms": gather_ms, "bytes_per_rank": 48 * b.W, "collective": "all_gather_into_tensor (NCCL)",
                               "note": "median of 5, timed alone after the passes; it is also inside every timed pass"}

@@ -18,6 +18,8 @@ for r in ranks:
     specs, ids = bench.build_specs(args, r, G)
     bw = fz.BatchedWorld(specs, ids)
     bw.set_tuning(cfg["mode"], cfg["chunk"])
+    if cfg.get("spec") and cfg["mode"] == "hybrid":
+        bw.set_spec(**cfg["spec"])
     snap = bw.snapshot()
     import ctypes as C
     gstat = [torch.zeros(g.spec.n_worlds, dtype=torch.int64, device="cuda") for g in bw.groups]
